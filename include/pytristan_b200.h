@@ -1,0 +1,138 @@
+/*
+ * pytristan_b200 — C-ABI of the B200 (sm_100a) differentiation hot path.
+ *
+ * Drop-in boundary.  The reference (pytristan 0.2a) is pure Python/NumPy and
+ * has no FFI; every entry point below replaces a NumPy call site of the reference or the
+ * operator layer its README announces (README.md:7-10,16,24-26).  The Python façade
+ * (pytristan_b200/*.py) binds these with ctypes; INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative pt_status on failure; the message of the
+ *     last failure on the calling thread is returned by pt_last_error();
+ *   - all data pointers are DEVICE pointers unless the name ends in _host; buffers are owned by
+ *     the caller; nothing is allocated inside;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is
+ *     enqueued asynchronously on it;
+ *   - a *field* on a grid with npts = (n0, .., n_{d-1}) is a flat FP64 vector in the reference's
+ *     own linearisation, axis 0 fastest (reference: grid.py:85-88).  For the axis k being
+ *     differentiated, before = prod(npts[:k]) (the stride of axis k), after = prod(npts[k+1:])
+ *     times the batch.  Element (a, i, b) sits at (a*n + i)*before + b.
+ */
+#ifndef PYTRISTAN_B200_H
+#define PYTRISTAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pt_stream_t;
+
+enum pt_status {
+  PT_OK = 0,
+  PT_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, unsupported value) */
+  PT_ERR_CUDA = -2,      /* a CUDA runtime call or launch failed */
+  PT_ERR_UNSUPPORTED = -3 /* valid request the library has no kernel for */
+};
+
+/* scale vector addressing for pt_dense_apply's fused epilogue */
+enum pt_scale_mode {
+  PT_SCALE_NONE = 0,
+  PT_SCALE_ROW = 1,    /* scale[i],            i = output index along the differentiated axis */
+  PT_SCALE_AFTER = 2,  /* scale[a % scale_len], a = index over the slower axes (and batch)     */
+  PT_SCALE_BEFORE = 3  /* scale[b],            b = index over the faster axes                  */
+};
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* pt_last_error(void);
+int pt_version(void);
+/* SM count and compute capability of the current device. */
+int pt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K5: node and grid generators (replace grid.py:75-77, :205, :83-88) ------------------- */
+/* x[i] = fl(fl(i*step)+start), step = fl(fl(stop-start)/(n-1)), x[n-1] = stop: NumPy's
+ * linspace arithmetic (numpy/_core/function_base.py), used by the reference at grid.py:205. */
+int pt_gen_linspace(double* x, double start, double stop, int64_t n, pt_stream_t stream);
+/* Chebyshev-Gauss-Lobatto nodes x_j = cos(fl(fl(j*pi)/(n-1))), descending (grid.py:75);
+ * if mapped != 0 additionally fl(fl(fl(fl(1-x)/2)*fl(xmax-xmin))+xmin) (grid.py:77). */
+int pt_gen_cheb(double* x, int64_t n, int mapped, double xmin, double xmax, pt_stream_t stream);
+/* In-place affine map of reference nodes, the arithmetic of grid.py:77 bit for bit. */
+int pt_cheb_map(double* x, int64_t n, double xmin, double xmax, pt_stream_t stream);
+/* Expand ndim 1-D axis arrays into the reference Grid layout (grid.py:83-88): out is
+ * (ndim, P) row-major, P = prod(npts), out[d][l] = axis_d[(l / prod(npts[:d])) % npts[d]].
+ * `axes` holds the axis arrays back to back (sum(npts) elements of elem_size bytes);
+ * npts_host is a HOST array of ndim entries.  elem_size in {1,2,4,8,16}: pure data movement. */
+int pt_grid_expand(const void* axes, const int64_t* npts_host, int ndim, int elem_size,
+                   void* out, pt_stream_t stream);
+/* Strided gather of the 1-D nodes of one axis out of a Grid row (grid.py:277-280). */
+int pt_grid_axpoints(const double* grid_row, int64_t stride, int64_t n, double* x,
+                     pt_stream_t stream);
+
+/* ---- K6: operator generators (operator layer announced at README.md:7-10,16) -------------- */
+/* Chebyshev collocation differentiation matrix of the given order on the nodes x (any affine
+ * image of the CGL set, either orientation).  D is n*n row-major.  Recursion of Welfert with
+ * the negative-sum diagonal, sequential summation order (oracle/operators.py:cheb_mat). */
+int pt_gen_chebmat(const double* x, int n, int order, double* D, pt_stream_t stream);
+/* Fourier spectral differentiation matrix (order 1 or 2) for n equispaced periodic nodes on a
+ * period `period`.  D is n*n row-major, circulant (oracle/operators.py:four_mat). */
+int pt_gen_fourmat(int n, double period, int order, double* D, pt_stream_t stream);
+/* Fornberg finite-difference weights, one row per node, in banded row-start layout:
+ * start[i] = clip(i - floor(w/2), 0, n - wmax) (periodic: i - floor(w/2), wrapped by the
+ * kernels), W[i*wmax + s] multiplies x[start[i] + s].  w = 2*floor((order+1)/2) - 1 + accuracy
+ * nodes for interior rows, order+accuracy nodes for one-sided boundary rows,
+ * wmax = max of the two (periodic: wmax = w).  If uniform != 0 the weights are generated on
+ * integer offsets and scaled by h^-order (h given), so that all interior rows are identical.
+ * (oracle/operators.py:findiff_band). */
+int pt_gen_fornberg(const double* x, int n, int order, int accuracy, int periodic, int uniform,
+                    double h, int32_t* start, double* W, int wmax, pt_stream_t stream);
+/* Banded row-start form -> dense n*n row-major matrix (zeros off the band). */
+int pt_band_to_dense(const double* W, const int32_t* start, int wmax, int n, int periodic,
+                     double* D, pt_stream_t stream);
+/* Explicit Kronecker lifting kron(I_after, kron(D, I_before)) for small grids; L is P*P
+ * row-major with P = after*n*before. */
+int pt_kron_lift(const double* D, int n, int64_t before, int64_t after, double* L,
+                 pt_stream_t stream);
+
+/* ---- K1/K2: dense operator application (FP64 tensor cores, DMMA m8n8k4) ------------------- */
+/* Number of doubles of the packed (fragment-major) copy of an n_out*n_in operator. */
+int64_t pt_packed_size(int n_out, int n_in);
+/* Pack a row-major operator (leading dimension ldD) into the layout the apply kernels read:
+ * [ceil(n_in/4)][8*ceil(n_out/8)][4], zero padded. */
+int pt_operator_pack(const double* D, int n_out, int n_in, int64_t ldD, double* packed,
+                     pt_stream_t stream);
+/* Y[a,:,b] = alpha * scale * (D @ U[a,:,b]) + beta * Y[a,:,b] for all a < after, b < before.
+ * U is (after, n_in, before), Y is (after, n_out, before), both C-contiguous.  before == 1
+ * (axis 0 of a grid) selects the contiguous-axis kernel (K2), before > 1 the strided-panel
+ * kernel (K1); neither transposes U or Y.  scale may be NULL (mode PT_SCALE_NONE). */
+int pt_dense_apply(const double* packed, int n_out, int n_in, const double* U, double* Y,
+                   int64_t after, int64_t before, double alpha, double beta,
+                   const double* scale, int scale_mode, int64_t scale_len, pt_stream_t stream);
+
+/* ---- K3/K4: banded (finite-difference) application --------------------------------------- */
+/* Y[a,i,b] = alpha * sum_s W[i*wmax+s] * U[a, start[i]+s, b] + beta * Y[a,i,b].
+ * If wuni != NULL, rows lo <= i < hi are canonical interior rows: their weights are the
+ * w_uni entries of wuni (HOST pointer, w_uni <= 16) applied at offset i - floor(w_uni/2);
+ * the kernels then keep those weights in registers.  periodic != 0 wraps indices modulo n. */
+int pt_stencil_apply(const double* W, const int32_t* start, int wmax, int n, const double* U,
+                     double* Y, int64_t after, int64_t before, int periodic,
+                     const double* wuni_host, int w_uni, int lo, int hi, double alpha,
+                     double beta, pt_stream_t stream);
+
+/* ---- K7: pencil-transpose pack/unpack (multi-GPU) ----------------------------------------- */
+/* Generic 3-D permutation copy used on both sides of the all-to-all: in is (d2, d1, d0)
+ * C-contiguous; out[perm] = in, perm one of the 6 axis orders encoded as p0 + 3*p1 + 9*p2
+ * where output axis j (slowest first) is input axis p_j. */
+int pt_permute3d(const double* in, double* out, int64_t d2, int64_t d1, int64_t d0, int perm,
+                 pt_stream_t stream);
+
+/* ---- measurement helper ------------------------------------------------------------------ */
+/* Register-resident DMMA loop: the FP64 tensor-core roofline denominator measured on the box.
+ * Writes achieved TFLOP/s to *tflops_host. */
+int pt_measure_dmma_peak(double* tflops_host, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYTRISTAN_B200_H */

@@ -1,0 +1,118 @@
+"""ctypes binding of the C-ABI library (include/pytristan_b200.h) and the device plumbing.
+
+PyTorch is used only for device memory, streams and host<->device copies; every computation
+goes through ``libpytristan_b200.so``.  There is no CPU fallback: without the library or
+without a CUDA device the calls below raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpytristan_b200.so")
+
+_c_i32 = ctypes.c_int
+_c_i64 = ctypes.c_int64
+_c_f64 = ctypes.c_double
+_c_ptr = ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/pytristan_b200.h one to one
+SIGNATURES = {
+    "pt_last_error": (ctypes.c_char_p, []),
+    "pt_version": (_c_i32, []),
+    "pt_device_info": (_c_i32, [ctypes.POINTER(_c_i32)] * 3),
+    "pt_gen_linspace": (_c_i32, [_c_ptr, _c_f64, _c_f64, _c_i64, _c_ptr]),
+    "pt_gen_cheb": (_c_i32, [_c_ptr, _c_i64, _c_i32, _c_f64, _c_f64, _c_ptr]),
+    "pt_cheb_map": (_c_i32, [_c_ptr, _c_i64, _c_f64, _c_f64, _c_ptr]),
+    "pt_grid_expand": (_c_i32, [_c_ptr, ctypes.POINTER(_c_i64), _c_i32, _c_i32, _c_ptr, _c_ptr]),
+    "pt_grid_axpoints": (_c_i32, [_c_ptr, _c_i64, _c_i64, _c_ptr, _c_ptr]),
+    "pt_gen_chebmat": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr]),
+    "pt_gen_fourmat": (_c_i32, [_c_i32, _c_f64, _c_i32, _c_ptr, _c_ptr]),
+    "pt_gen_fornberg": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_f64, _c_ptr,
+                                 _c_ptr, _c_i32, _c_ptr]),
+    "pt_band_to_dense": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr]),
+    "pt_kron_lift": (_c_i32, [_c_ptr, _c_i32, _c_i64, _c_i64, _c_ptr, _c_ptr]),
+    "pt_packed_size": (_c_i64, [_c_i32, _c_i32]),
+    "pt_operator_pack": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_i64, _c_ptr, _c_ptr]),
+    "pt_dense_apply": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64,
+                                _c_f64, _c_ptr, _c_i32, _c_i64, _c_ptr]),
+    "pt_stencil_apply": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64,
+                                  _c_i32, ctypes.POINTER(_c_f64), _c_i32, _c_i32, _c_i32, _c_f64,
+                                  _c_f64, _c_ptr]),
+    "pt_permute3d": (_c_i32, [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_i64, _c_i32, _c_ptr]),
+    "pt_measure_dmma_peak": (_c_i32, [ctypes.POINTER(_c_f64), _c_i32]),
+}
+
+SCALE_NONE, SCALE_ROW, SCALE_AFTER, SCALE_BEFORE = 0, 1, 2, 3
+
+_lib = None
+
+
+class PytristanCudaError(RuntimeError):
+    """A C-ABI call failed; the message is the library's pt_last_error()."""
+
+
+def load():
+    """Load (once) and return the ctypes handle of the C-ABI library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m pytristan_b200.build` "
+            "(pytristan_b200 has no CPU fallback)"
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().pt_last_error()
+        raise PytristanCudaError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def torch_mod():
+    import torch
+
+    return torch
+
+
+def require_cuda():
+    """Return ``torch`` after making sure a CUDA device is usable; raise otherwise."""
+    torch = torch_mod()
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "pytristan_b200 needs a CUDA device (B200, sm_100a): there is no CPU fallback"
+        )
+    load()
+    return torch
+
+
+def stream_ptr():
+    torch = torch_mod()
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dptr(t):
+    """Device pointer of a torch tensor as c_void_p (None for None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def to_device(arr, dtype=None):
+    """Host ndarray -> contiguous CUDA tensor (reinterpreting unsupported dtypes as bytes is the
+    caller's business)."""
+    torch = require_cuda()
+    a = np.ascontiguousarray(arr, dtype=dtype)
+    return torch.from_numpy(a).cuda(non_blocking=False)
+
+
+def empty(shape, dtype=None):
+    torch = require_cuda()
+    return torch.empty(shape, dtype=dtype or torch.float64, device="cuda")

@@ -1,0 +1,425 @@
+// K1/K2 — dense differentiation-operator application on FP64 tensor cores (DMMA m8n8k4).
+//
+//   Y[a, :, b] = alpha * scale * (D @ U[a, :, b]) + beta * Y[a, :, b]
+//
+// U is (after, n_in, before) C-contiguous, i.e. a field in the reference Grid's linearisation
+// (axis 0 fastest, reference grid.py:85-88) seen from the differentiated axis.  The operator D
+// is always the A operand of the MMA (M = output index i along the axis); the field supplies
+// the B operand with its columns being the flattened (a, b) index space:
+//   K1 (before > 1): column nn = a*before + b, k-stride = before   -> smem tile [k][n]
+//   K2 (before == 1): column nn = a,            k-stride = 1        -> smem tile [n][k]
+// Neither case transposes U or Y in global memory.
+//
+// D is read from the packed fragment-major copy [k/4][8*ceil(n_out/8)][4] (pt_operator_pack):
+// an (8-row, 4-k) block is 256 contiguous bytes, lane l of a warp reads double l, which is
+// exactly the m8n8k4 A fragment (row = l/4, k = l%4) — conflict-free without padding.
+// Field tiles are staged with cp.async (16-byte when alignment allows, else 8-byte) into a
+// padded layout (pitch = 4 mod 16 doubles) that makes the B-fragment reads conflict-free.
+//
+// FP64 tensor cores on sm_100a are warp-level only (tcgen05 has no f64 kind), so accumulators
+// live in registers; see DESIGN.md §4.1 for the roofline this kernel is judged against.
+#include "common.cuh"
+
+namespace {
+
+struct DenseParams {
+  const double* __restrict__ Dp;
+  const double* __restrict__ U;
+  double* __restrict__ Y;
+  const double* __restrict__ scale;
+  int n_out, n_in;
+  int MP, KP;            // padded rows of the packed operator, number of k-panels
+  int mt_per_block;      // m-tiles (8 rows) handled by one CTA
+  int m_blocks;
+  int64_t before;
+  int64_t NN;            // number of field columns: after*before (K1) or after (K2)
+  int64_t slab_in;       // n_in*before: distance between consecutive `a` slabs of U
+  int64_t slab_out;      // n_out*before
+  double alpha, beta;
+  int scale_mode;
+  int64_t scale_len;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// WARPS_M x WARPS_N warps, each owning up to WM m-tiles x WN n-tiles of 8x8.
+template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16>
+struct Cfg {
+  static constexpr int NT = WARPS_M * WARPS_N * 32;
+  static constexpr int BM = WARPS_M * WM * 8;
+  static constexpr int BN = WARPS_N * WN * 8;
+  static constexpr int BK = BKP * 4;
+  static constexpr int A_STAGE = BKP * BM * 4;                     // doubles
+  static constexpr int PB = KCONTIG ? (BK + 4) : (BN + 4);          // pitch, = 4 mod 16
+  static constexpr int B_STAGE = KCONTIG ? BN * PB : BK * PB;       // doubles
+  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr size_t SMEM = size_t(STAGES) * STAGE * sizeof(double);
+};
+
+template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1)
+dense_apply_kernel(const DenseParams p) {
+  using C = Cfg<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16>;
+  extern __shared__ __align__(16) double smem[];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int wn = warp % WARPS_N;
+  const int wm = warp / WARPS_N;
+  const int g = lane >> 2;  // fragment row (A) / column (B)
+  const int t = lane & 3;   // fragment k index
+
+  // block -> (m_block fastest, n_block): CTAs sharing a field tile run together (L2 reuse of U)
+  const int m_block = blockIdx.x % p.m_blocks;
+  const int64_t n_block = blockIdx.x / p.m_blocks;
+  const int mtiles_total = p.MP >> 3;
+  const int mt0 = m_block * p.mt_per_block;
+  const int mt_count = min(p.mt_per_block, mtiles_total - mt0);
+  const int m0 = mt0 * 8;
+  const int rows_blk = mt_count * 8;
+  const int64_t n0 = n_block * C::BN;
+
+  // this warp's m-tiles: balanced split of the CTA's mt_count tiles over WARPS_M warps
+  const int q = (mt_count + WARPS_M - 1) / WARPS_M;
+  const int my_mt0 = wm * q;
+  const int my_mt = max(0, min(q, mt_count - my_mt0));
+
+  const int nchunks = (p.KP + BKP - 1) / BKP;
+
+  // ---- per-thread constants of the field-tile loader --------------------------------------
+  constexpr int EPC = VEC16 ? 2 : 1;  // doubles per cp.async
+  // K1: columns are contiguous in memory.  One thread always serves the same column chunk.
+  constexpr int CPR1 = C::BN / EPC;           // chunks per k-row
+  constexpr int RPP1 = C::NT / CPR1;          // k-rows per pass
+  static_assert(KCONTIG || (C::NT % CPR1 == 0 && C::BK % RPP1 == 0), "K1 loader shape");
+  // K2: k is contiguous in memory.
+  constexpr int CPR2 = C::BK / EPC;           // chunks per column (field row a)
+  constexpr int RPP2 = C::NT / CPR2;          // columns per pass
+  static_assert(!KCONTIG || (C::NT % CPR2 == 0 && C::BN % RPP2 == 0), "K2 loader shape");
+
+  const double* b_src = p.U;
+  bool b_col_ok = false;
+  int b_cc = 0, b_r0 = 0;
+  if (!KCONTIG) {
+    b_cc = tid % CPR1;
+    b_r0 = tid / CPR1;
+    const int64_t nn = n0 + int64_t(b_cc) * EPC;
+    b_col_ok = nn < p.NN;
+    if (b_col_ok) {
+      const int64_t a = nn / p.before;
+      const int64_t b = nn - a * p.before;
+      b_src = p.U + a * p.slab_in + b;
+    }
+  } else {
+    b_cc = tid % CPR2;  // chunk along k
+    b_r0 = tid / CPR2;  // first column served
+  }
+
+  auto load_stage = [&](int stage, int chunk) {
+    double* As = smem + size_t(stage) * C::STAGE;
+    double* Bs = As + C::A_STAGE;
+    const int kp0 = chunk * BKP;
+    // operator tile: BKP panels of rows_blk*4 contiguous doubles
+    for (int idx = tid; idx < BKP * C::BM * 2; idx += C::NT) {
+      const int pp = idx / (C::BM * 2);
+      const int c = idx - pp * (C::BM * 2);
+      const bool ok = (kp0 + pp < p.KP) && ((c >> 1) < rows_blk);
+      const double* src = ok ? p.Dp + (size_t(kp0 + pp) * p.MP + m0) * 4 + c * 2 : p.Dp;
+      cp_async16(As + (pp * C::BM * 4) + c * 2, src, ok ? 16 : 0);
+    }
+    const int k0 = kp0 * 4;
+    if (!KCONTIG) {
+#pragma unroll
+      for (int r = 0; r < C::BK / RPP1; ++r) {
+        const int kr = b_r0 + r * RPP1;
+        const int k = k0 + kr;
+        const bool ok = b_col_ok && (k < p.n_in);
+        const double* src = ok ? b_src + int64_t(k) * p.before : p.U;
+        double* dst = Bs + kr * C::PB + b_cc * EPC;
+        if (VEC16) cp_async16(dst, src, ok ? 16 : 0);
+        else cp_async8(dst, src, ok ? 8 : 0);
+      }
+    } else {
+      const int k = k0 + b_cc * EPC;
+#pragma unroll
+      for (int r = 0; r < C::BN / RPP2; ++r) {
+        const int col = b_r0 + r * RPP2;
+        const int64_t nn = n0 + col;
+        const bool ok = (nn < p.NN) && (k < p.n_in);
+        const double* src = ok ? p.U + nn * p.n_in + k : p.U;
+        double* dst = Bs + col * C::PB + b_cc * EPC;
+        if (VEC16) {
+          const int bytes = ok ? ((k + 1 < p.n_in) ? 16 : 8) : 0;
+          cp_async16(dst, src, bytes);
+        } else {
+          cp_async8(dst, src, ok ? 8 : 0);
+        }
+      }
+    }
+  };
+
+  double acc[WM][WN][2];
+#pragma unroll
+  for (int i = 0; i < WM; ++i)
+#pragma unroll
+    for (int j = 0; j < WN; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+  // ---- prologue: STAGES-1 chunks in flight ---------------------------------------------------
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nchunks) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  // ---- main loop ----------------------------------------------------------------------------
+  for (int kc = 0; kc < nchunks; ++kc) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = kc + STAGES - 1;
+      if (nxt < nchunks) load_stage(nxt % STAGES, nxt);
+      cp_async_commit();
+    }
+    const double* As = smem + size_t(kc % STAGES) * C::STAGE;
+    const double* Bs = As + C::A_STAGE;
+    const int kp0 = kc * BKP;
+#pragma unroll
+    for (int pp = 0; pp < BKP; ++pp) {
+      if (kp0 + pp < p.KP) {
+        double af[WM], bf[WN];
+#pragma unroll
+        for (int i = 0; i < WM; ++i)
+          if (i < my_mt) af[i] = As[(pp * C::BM + (my_mt0 + i) * 8) * 4 + lane];
+#pragma unroll
+        for (int j = 0; j < WN; ++j) {
+          const int col = (wn * WN + j) * 8 + g;
+          bf[j] = KCONTIG ? Bs[col * C::PB + pp * 4 + t] : Bs[(pp * 4 + t) * C::PB + col];
+        }
+#pragma unroll
+        for (int i = 0; i < WM; ++i)
+          if (i < my_mt) {
+#pragma unroll
+            for (int j = 0; j < WN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+          }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue: Y = alpha*scale*acc + beta*Y ----------------------------------------------------
+  const bool use_beta = (p.beta != 0.0);
+#pragma unroll
+  for (int j = 0; j < WN; ++j) {
+    const int64_t nn = n0 + (wn * WN + j) * 8 + 2 * t;  // this thread's first column
+    if (nn >= p.NN) continue;
+    const bool two = (nn + 1 < p.NN);
+    int64_t a0, b0, a1, b1;  // (a, b) of the two columns
+    if (KCONTIG) {
+      a0 = nn; b0 = 0; a1 = nn + 1; b1 = 0;
+    } else {
+      a0 = nn / p.before; b0 = nn - a0 * p.before;
+      if (b0 + 1 < p.before) { a1 = a0; b1 = b0 + 1; } else { a1 = a0 + 1; b1 = 0; }
+    }
+    double s0 = p.alpha, s1 = p.alpha;
+    if (p.scale_mode == PT_SCALE_AFTER) {
+      s0 *= p.scale[a0 % p.scale_len];
+      if (two) s1 *= p.scale[a1 % p.scale_len];
+    } else if (p.scale_mode == PT_SCALE_BEFORE) {
+      s0 *= p.scale[b0];
+      if (two) s1 *= p.scale[b1];
+    }
+    double* y0 = p.Y + a0 * p.slab_out + b0;
+    double* y1 = p.Y + a1 * p.slab_out + b1;
+#pragma unroll
+    for (int i = 0; i < WM; ++i) {
+      if (i >= my_mt) continue;
+      const int row = m0 + (my_mt0 + i) * 8 + g;
+      if (row >= p.n_out) continue;
+      double r0 = s0, r1 = s1;
+      if (p.scale_mode == PT_SCALE_ROW) { const double sr = p.scale[row]; r0 *= sr; r1 *= sr; }
+      double v0 = r0 * acc[i][j][0];
+      double v1 = r1 * acc[i][j][1];
+      const int64_t off = int64_t(row) * p.before;
+      if (!KCONTIG && VEC16) {
+        // before is even and nn is even: both columns are adjacent in the same slab
+        double2* dst = reinterpret_cast<double2*>(y0 + off);
+        if (use_beta) { const double2 o = *dst; v0 += p.beta * o.x; v1 += p.beta * o.y; }
+        *dst = make_double2(v0, v1);
+      } else {
+        if (use_beta) v0 += p.beta * y0[off];
+        y0[off] = v0;
+        if (two) {
+          if (use_beta) v1 += p.beta * y1[off];
+          y1[off] = v1;
+        }
+      }
+    }
+  }
+}
+
+// fragment-major packing: packed[((j/4)*MP + i)*4 + j%4] = D[i*ldD + j], zero elsewhere
+__global__ void pack_operator_kernel(const double* __restrict__ D, int n_out, int n_in,
+                                     int64_t ldD, int MP, int KP, double* __restrict__ packed) {
+  const int64_t total = int64_t(KP) * MP * 4;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int kk = int(idx & 3);
+    const int64_t r = idx >> 2;
+    const int i = int(r % MP);
+    const int kp = int(r / MP);
+    const int j = kp * 4 + kk;
+    packed[idx] = (i < n_out && j < n_in) ? D[int64_t(i) * ldD + j] : 0.0;
+  }
+}
+
+template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16>
+int launch_cfg(DenseParams& p, cudaStream_t stream) {
+  using C = Cfg<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16>;
+  auto kern = dense_apply_kernel<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  PT_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
+    attr_set[dev] = true;
+  }
+  const int mtiles = p.MP / 8;
+  const int max_mt = WARPS_M * WM;
+  p.m_blocks = (mtiles + max_mt - 1) / max_mt;
+  p.mt_per_block = (mtiles + p.m_blocks - 1) / p.m_blocks;
+  p.m_blocks = (mtiles + p.mt_per_block - 1) / p.mt_per_block;
+  const int64_t n_blocks = (p.NN + C::BN - 1) / C::BN;
+  const int64_t grid = n_blocks * p.m_blocks;
+  if (grid <= 0) return PT_OK;
+  if (grid > 2147483647LL) return pt::fail(PT_ERR_UNSUPPORTED, "pt_dense_apply: grid too large");
+  kern<<<unsigned(grid), C::NT, C::SMEM, stream>>>(p);
+  return pt::check_launch("pt_dense_apply");
+}
+
+template <bool KCONTIG, bool VEC16>
+int launch_shape(DenseParams& p, cudaStream_t stream) {
+  // one configuration for now: 8 warps, 128x128 CTA tile (64x32 per warp), BK = 16, 4 stages
+  return launch_cfg<2, 4, 8, 4, 4, 4, KCONTIG, VEC16>(p, stream);
+}
+
+inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
+
+}  // namespace
+
+extern "C" int64_t pt_packed_size(int n_out, int n_in) {
+  if (n_out <= 0 || n_in <= 0) return 0;
+  const int64_t MP = 8 * ((int64_t(n_out) + 7) / 8);
+  const int64_t KP = (int64_t(n_in) + 3) / 4;
+  return KP * MP * 4;
+}
+
+extern "C" int pt_operator_pack(const double* D, int n_out, int n_in, int64_t ldD, double* packed,
+                                pt_stream_t stream) {
+  PT_REQUIRE(D && packed, "pt_operator_pack: null pointer");
+  PT_REQUIRE(n_out > 0 && n_in > 0 && ldD >= n_in, "pt_operator_pack: bad shape %d x %d ld %lld",
+             n_out, n_in, (long long)ldD);
+  const int MP = 8 * ((n_out + 7) / 8);
+  const int KP = (n_in + 3) / 4;
+  const int64_t total = int64_t(KP) * MP * 4;
+  const int threads = 256;
+  int64_t nb = (total + threads - 1) / threads;
+  const int blocks = int(nb < 148 * 16 ? nb : 148 * 16);
+  pack_operator_kernel<<<blocks, threads, 0, pt::as_stream(stream)>>>(D, n_out, n_in, ldD, MP, KP,
+                                                                     packed);
+  return pt::check_launch("pt_operator_pack");
+}
+
+extern "C" int pt_dense_apply(const double* packed, int n_out, int n_in, const double* U, double* Y,
+                              int64_t after, int64_t before, double alpha, double beta,
+                              const double* scale, int scale_mode, int64_t scale_len,
+                              pt_stream_t stream) {
+  PT_REQUIRE(packed && U && Y, "pt_dense_apply: null pointer");
+  PT_REQUIRE(n_out > 0 && n_in > 0, "pt_dense_apply: bad operator shape %d x %d", n_out, n_in);
+  PT_REQUIRE(after >= 0 && before >= 1, "pt_dense_apply: bad field shape after=%lld before=%lld",
+             (long long)after, (long long)before);
+  PT_REQUIRE(scale_mode >= PT_SCALE_NONE && scale_mode <= PT_SCALE_BEFORE,
+             "pt_dense_apply: bad scale_mode %d", scale_mode);
+  PT_REQUIRE(scale_mode == PT_SCALE_NONE || scale != nullptr, "pt_dense_apply: scale is null");
+  PT_REQUIRE(scale_mode != PT_SCALE_AFTER || scale_len > 0, "pt_dense_apply: scale_len must be > 0");
+  PT_REQUIRE(U != Y, "pt_dense_apply: in-place application is not supported");
+  if (after == 0) return PT_OK;
+
+  DenseParams p;
+  p.Dp = packed; p.U = U; p.Y = Y; p.scale = scale;
+  p.n_out = n_out; p.n_in = n_in;
+  p.MP = 8 * ((n_out + 7) / 8);
+  p.KP = (n_in + 3) / 4;
+  p.before = before;
+  p.NN = after * before;
+  p.slab_in = int64_t(n_in) * before;
+  p.slab_out = int64_t(n_out) * before;
+  p.alpha = alpha; p.beta = beta;
+  p.scale_mode = scale_mode; p.scale_len = scale_len > 0 ? scale_len : 1;
+  p.m_blocks = 1; p.mt_per_block = 1;
+  cudaStream_t st = pt::as_stream(stream);
+  if (before == 1) {
+    const bool vec = (n_in % 2 == 0) && aligned16(U);
+    return vec ? launch_shape<true, true>(p, st) : launch_shape<true, false>(p, st);
+  }
+  const bool vec = (before % 2 == 0) && aligned16(U) && aligned16(Y);
+  return vec ? launch_shape<false, true>(p, st) : launch_shape<false, false>(p, st);
+}
+
+// ---- FP64 tensor-core peak (roofline denominator) ----------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+  double c[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+  const double a = 0.5 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dmma(c[i][0], c[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int pt_measure_dmma_peak(double* tflops_host, int iters) {
+  PT_REQUIRE(tflops_host && iters > 0, "pt_measure_dmma_peak: bad argument");
+  const int grid = pt::sm_count() * 2;
+  double* out = nullptr;
+  PT_CUDA(cudaMalloc(&out, sizeof(double) * grid * 256));
+  cudaEvent_t e0, e1;
+  PT_CUDA(cudaEventCreate(&e0));
+  PT_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int r = 0; r < 5; ++r) {
+    PT_CUDA(cudaEventRecord(e0));
+    dmma_peak_kernel<<<grid, 256>>>(out, iters);
+    PT_CUDA(cudaEventRecord(e1));
+    PT_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    PT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  const double flops = 2.0 * 256.0 * 16.0 * double(iters) * 8.0 * grid;
+  *tflops_host = flops / (best * 1e-3) * 1e-12;
+  return PT_OK;
+}

@@ -1,0 +1,357 @@
+// K3/K4 — banded (finite-difference) operator application, HBM-bound.
+//
+//   Y[a, i, b] = alpha * sum_s W[i][s] * U[a, start[i]+s, b] + beta * Y[a, i, b]
+//
+// Three kernels:
+//   stencil_table      any band (per-row weights, one-sided closures, periodic wrap); one thread
+//                      per output point.  Used for non-uniform (mapped) axes and as the
+//                      boundary-row path of the two fast kernels.
+//   stencil_strided    (K4) before > 1, canonical interior rows with uniform weights: threads
+//                      run along the contiguous index b (16-byte vectors), march along the
+//                      differentiated axis with a register sliding window: every U element is
+//                      loaded once and reused w times, every Y element written once (16 B/pt).
+//   stencil_contig     (K3) before == 1: a (rows x segment) tile with halo is staged in shared
+//                      memory with coalesced 16-byte loads; each lane produces two adjacent
+//                      points from five conflict-free LDS.128.
+// Algorithmic traffic is 16 bytes per point per derivative (read U once, write Y once);
+// DESIGN.md §4.2 states the roofline.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAXW = 16;
+
+struct UniWeights { double w[MAXW]; };
+
+struct StencilParams {
+  const double* __restrict__ W;
+  const int32_t* __restrict__ start;
+  const double* __restrict__ U;
+  double* __restrict__ Y;
+  int wmax, n;
+  int64_t after, before;
+  int periodic;
+  int lo, hi;  // canonical interior rows [lo, hi) (fast kernels); table rows elsewhere
+  double alpha, beta;
+};
+
+__device__ __forceinline__ int wrap_index(int j, int n) {
+  j %= n;
+  return j < 0 ? j + n : j;
+}
+
+// one table row for one column: base points at U[a, 0, b]
+__device__ __forceinline__ double table_point(const StencilParams& p, const double* base, int i) {
+  const double* w = p.W + int64_t(i) * p.wmax;
+  const int s0 = p.start[i];
+  double acc = 0.0;
+  for (int s = 0; s < p.wmax; ++s) {
+    int j = s0 + s;
+    if (p.periodic) j = wrap_index(j, p.n);
+    acc = fma(w[s], base[int64_t(j) * p.before], acc);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void store_point(const StencilParams& p, double* y, double v) {
+  v *= p.alpha;
+  if (p.beta != 0.0) v = fma(p.beta, *y, v);
+  *y = v;
+}
+
+// ---- generic table kernel ------------------------------------------------------------------------
+// rows r = a*n + i in [row_lo, row_hi) restricted to i outside [skip_lo, skip_hi)
+__global__ void __launch_bounds__(256) stencil_table_kernel(const StencilParams p, int skip_lo,
+                                                             int skip_hi) {
+  // rows that need the table per slab: i in [0, skip_lo) U [skip_hi, n)
+  const int per_slab = skip_lo + (p.n - skip_hi);
+  const int64_t total = p.after * int64_t(per_slab) * p.before;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t b = idx % p.before;
+    const int64_t r = idx / p.before;
+    const int ii = int(r % per_slab);
+    const int64_t a = r / per_slab;
+    const int i = ii < skip_lo ? ii : ii - skip_lo + skip_hi;
+    const double* base = p.U + a * int64_t(p.n) * p.before + b;
+    const double v = table_point(p, base, i);
+    store_point(p, p.Y + (a * int64_t(p.n) + i) * p.before + b, v);
+  }
+}
+
+// ---- K4: strided axis, register sliding window -----------------------------------------------------
+template <int V> struct Vec;
+template <> struct Vec<1> { using T = double; };
+template <> struct Vec<2> { using T = double2; };
+
+__device__ __forceinline__ double vfma(double w, double x, double acc) { return fma(w, x, acc); }
+__device__ __forceinline__ double2 vfma(double w, double2 x, double2 acc) {
+  return make_double2(fma(w, x.x, acc.x), fma(w, x.y, acc.y));
+}
+__device__ __forceinline__ double vzero(double) { return 0.0; }
+__device__ __forceinline__ double2 vzero(double2) { return make_double2(0.0, 0.0); }
+__device__ __forceinline__ double vaxpby(double al, double v, double be, double y) {
+  return fma(be, y, al * v);
+}
+__device__ __forceinline__ double2 vaxpby(double al, double2 v, double be, double2 y) {
+  return make_double2(fma(be, y.x, al * v.x), fma(be, y.y, al * v.y));
+}
+__device__ __forceinline__ double vscale(double al, double v) { return al * v; }
+__device__ __forceinline__ double2 vscale(double al, double2 v) {
+  return make_double2(al * v.x, al * v.y);
+}
+
+// Thread = one vector column (V doubles along b) of one slab a, rows [c0, c1) of the canonical
+// range.  grid.x = column chunks, grid.y = i-chunks, grid.z = a (folded).
+template <int W, int V>
+__global__ void __launch_bounds__(128) stencil_strided_kernel(const StencilParams p,
+                                                               const UniWeights uw, int ichunk,
+                                                               int64_t ncolv) {
+  using T = typename Vec<V>::T;
+  constexpr int HW = W / 2;
+  const int64_t colv = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;  // vector column in slab
+  if (colv >= ncolv) return;
+  const int64_t a = blockIdx.z;
+  const int64_t stride = p.before / V;  // row stride in vectors
+  const T* __restrict__ u = reinterpret_cast<const T*>(p.U + a * int64_t(p.n) * p.before) + colv;
+  T* __restrict__ y = reinterpret_cast<T*>(p.Y + a * int64_t(p.n) * p.before) + colv;
+  const int c0 = p.lo + blockIdx.y * ichunk;
+  const int c1 = min(c0 + ichunk, p.hi);
+  if (c0 >= c1) return;
+  const int n = p.n;
+  const bool use_beta = p.beta != 0.0;
+
+  double w[W];
+#pragma unroll
+  for (int s = 0; s < W; ++s) w[s] = uw.w[s];
+
+  auto row = [&](int j) -> T {
+    if (p.periodic) { if (j < 0) j += n; else if (j >= n) j -= n; }
+    return u[int64_t(j) * stride];
+  };
+
+  T v[2 * W - 1];
+#pragma unroll
+  for (int s = 0; s < W - 1; ++s) v[s] = row(c0 - HW + s);
+
+  for (int i = c0; i < c1; i += W) {
+    // W independent loads in flight per thread
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+      const int j = i + q + HW;
+      if (i + q < c1) v[W - 1 + q] = row(j);
+    }
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+      if (i + q < c1) {
+        T acc = vzero(T());
+#pragma unroll
+        for (int s = 0; s < W; ++s) acc = vfma(w[s], v[q + s], acc);
+        T* dst = y + int64_t(i + q) * stride;
+        if (use_beta) *dst = vaxpby(p.alpha, acc, p.beta, *dst);
+        else *dst = vscale(p.alpha, acc);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < W - 1; ++s) v[s] = v[W + s];
+  }
+}
+
+// ---- K3: contiguous axis, shared-memory tile ---------------------------------------------------------
+// Block = 256 threads, tile = ROWS rows x TI points (TI even), halo HL = 4 doubles each side.
+// V = 2: 16-byte staging loads (n even, 16-byte aligned base); V = 1: 8-byte staging.
+template <int W, int V>
+__global__ void __launch_bounds__(256) stencil_contig_kernel(const StencilParams p,
+                                                              const UniWeights uw, int TI, int ROWS,
+                                                              int tiles_per_row) {
+  constexpr int HW = W / 2;
+  constexpr int HL = 4;
+  extern __shared__ __align__(16) double sm[];
+  const int pitch = TI + 2 * HL;
+  const int n = p.n;
+  const int64_t tile = blockIdx.x;
+  const int ti = int(tile % tiles_per_row);
+  const int64_t row0 = (tile / tiles_per_row) * ROWS;
+  const int i0 = ti * TI;
+  const int tid = threadIdx.x;
+
+  // ---- stage: ROWS x (TI + 8) doubles; chunk = V doubles
+  const int cpr = pitch / V;
+  for (int idx = tid; idx < ROWS * cpr; idx += 256) {
+    const int r = idx / cpr;
+    const int c = (idx - r * cpr) * V;      // offset inside the padded row
+    const int64_t a = row0 + r;
+    if (a >= p.after) continue;
+    int j = i0 - HL + c;                     // global index of the first double of the chunk
+    const double* rowp = p.U + a * int64_t(n);
+    double* dst = sm + r * pitch + c;
+    if (V == 2) {
+      double2 val = make_double2(0.0, 0.0);
+      if (j >= 0 && j + 1 < n) {
+        val = *reinterpret_cast<const double2*>(rowp + j);
+      } else if (p.periodic) {
+        val.x = rowp[wrap_index(j, n)];
+        val.y = rowp[wrap_index(j + 1, n)];
+      } else {
+        if (j >= 0 && j < n) val.x = rowp[j];
+        if (j + 1 >= 0 && j + 1 < n) val.y = rowp[j + 1];
+      }
+      *reinterpret_cast<double2*>(dst) = val;
+    } else {
+      double val = 0.0;
+      if (j >= 0 && j < n) val = rowp[j];
+      else if (p.periodic) val = rowp[wrap_index(j, n)];
+      *dst = val;
+    }
+  }
+  __syncthreads();
+
+  double w[W];
+#pragma unroll
+  for (int s = 0; s < W; ++s) w[s] = uw.w[s];
+  const bool use_beta = p.beta != 0.0;
+
+  // ---- compute: each item = 2 adjacent points
+  const int ipr = TI / 2;  // items per row
+  for (int idx = tid; idx < ROWS * ipr; idx += 256) {
+    const int r = idx / ipr;
+    const int li = (idx - r * ipr) * 2;   // local point index (even)
+    const int64_t a = row0 + r;
+    const int i = i0 + li;
+    if (a >= p.after || i >= n) continue;
+    const double* s = sm + r * pitch + li;  // s[0] is point i - HL
+    double v[10];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const double2 t2 = *reinterpret_cast<const double2*>(s + 2 * k);
+      v[2 * k] = t2.x; v[2 * k + 1] = t2.y;
+    }
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+      acc0 = fma(w[q], v[HL - HW + q], acc0);
+      acc1 = fma(w[q], v[HL - HW + 1 + q], acc1);
+    }
+    double* yp = p.Y + a * int64_t(n) + i;
+    const bool ok0 = (i >= p.lo && i < p.hi);
+    const bool ok1 = (i + 1 >= p.lo && i + 1 < p.hi);  // i + 1 < n implied by hi <= n
+    if (V == 2 && ok0 && ok1) {
+      double2 o = make_double2(p.alpha * acc0, p.alpha * acc1);
+      if (use_beta) {
+        const double2 old = *reinterpret_cast<const double2*>(yp);
+        o.x = fma(p.beta, old.x, o.x); o.y = fma(p.beta, old.y, o.y);
+      }
+      *reinterpret_cast<double2*>(yp) = o;
+    } else {
+      if (ok0) { double o = p.alpha * acc0; if (use_beta) o = fma(p.beta, yp[0], o); yp[0] = o; }
+      if (ok1) { double o = p.alpha * acc1; if (use_beta) o = fma(p.beta, yp[1], o); yp[1] = o; }
+    }
+  }
+}
+
+inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
+
+int launch_table(const StencilParams& p, int skip_lo, int skip_hi, cudaStream_t st) {
+  const int per_slab = skip_lo + (p.n - skip_hi);
+  const int64_t total = p.after * int64_t(per_slab) * p.before;
+  if (total <= 0) return PT_OK;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = int64_t(pt::sm_count()) * 32;
+  if (blocks > cap) blocks = cap;
+  stencil_table_kernel<<<unsigned(blocks), 256, 0, st>>>(p, skip_lo, skip_hi);
+  return pt::check_launch("pt_stencil_apply(table)");
+}
+
+template <int W>
+int launch_strided(const StencilParams& p, const UniWeights& uw, cudaStream_t st) {
+  const bool vec = (p.before % 2 == 0) && aligned16(p.U) && aligned16(p.Y);
+  const int V = vec ? 2 : 1;
+  const int64_t ncolv = p.before / V;
+  const int64_t gx = (ncolv + 127) / 128;
+  // split the marching axis only when there are too few columns to fill the GPU
+  const int64_t want = int64_t(pt::sm_count()) * 16;
+  const int rows = p.hi - p.lo;
+  int64_t ysplit = 1;
+  if (gx * p.after < want) ysplit = (want + gx * p.after - 1) / (gx * p.after);
+  int ichunk = int((rows + ysplit - 1) / ysplit);
+  if (ichunk < 8 * W) ichunk = 8 * W;         // keep halo re-reads below ~1/8
+  if (ichunk > rows) ichunk = rows;
+  const int gy = (rows + ichunk - 1) / ichunk;
+  PT_REQUIRE(gx <= 2147483647LL && gy <= 65535, "pt_stencil_apply: grid too large");
+  // grid.z is limited to 65535: fold larger `after` into several launches
+  for (int64_t a0 = 0; a0 < p.after; a0 += 65535) {
+    StencilParams q = p;
+    const int64_t na = (p.after - a0 < 65535) ? p.after - a0 : 65535;
+    q.U = p.U + a0 * int64_t(p.n) * p.before;
+    q.Y = p.Y + a0 * int64_t(p.n) * p.before;
+    q.after = na;
+    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)na);
+    if (vec) stencil_strided_kernel<W, 2><<<grid, 128, 0, st>>>(q, uw, ichunk, ncolv);
+    else stencil_strided_kernel<W, 1><<<grid, 128, 0, st>>>(q, uw, ichunk, ncolv);
+    int rc = pt::check_launch("pt_stencil_apply(strided)");
+    if (rc) return rc;
+  }
+  return PT_OK;
+}
+
+template <int W>
+int launch_contig(const StencilParams& p, const UniWeights& uw, cudaStream_t st) {
+  const bool vec = (p.n % 2 == 0) && aligned16(p.U) && aligned16(p.Y);
+  // tile: TI points per row segment (even), ROWS rows, about 4096 points per block
+  int TI = p.n + (p.n & 1);
+  if (TI > 2048) TI = 2048;
+  int ROWS = 4096 / TI;
+  if (ROWS > 5120 / (TI + 8)) ROWS = 5120 / (TI + 8);  // keep the tile under 40 KB of smem
+  if (ROWS < 1) ROWS = 1;
+  if (ROWS > p.after) ROWS = int(p.after);
+  const int tiles_per_row = (p.n + TI - 1) / TI;
+  const int64_t tiles = ((p.after + ROWS - 1) / ROWS) * tiles_per_row;
+  PT_REQUIRE(tiles <= 2147483647LL, "pt_stencil_apply: grid too large");
+  const size_t smem = size_t(ROWS) * (TI + 8) * sizeof(double);
+  if (vec) stencil_contig_kernel<W, 2><<<unsigned(tiles), 256, smem, st>>>(p, uw, TI, ROWS, tiles_per_row);
+  else stencil_contig_kernel<W, 1><<<unsigned(tiles), 256, smem, st>>>(p, uw, TI, ROWS, tiles_per_row);
+  return pt::check_launch("pt_stencil_apply(contig)");
+}
+
+template <int W>
+int launch_fast(const StencilParams& p, const UniWeights& uw, cudaStream_t st) {
+  int rc = (p.before == 1) ? launch_contig<W>(p, uw, st) : launch_strided<W>(p, uw, st);
+  if (rc) return rc;
+  return launch_table(p, p.lo, p.hi, st);  // boundary rows
+}
+
+}  // namespace
+
+extern "C" int pt_stencil_apply(const double* W, const int32_t* start, int wmax, int n,
+                                const double* U, double* Y, int64_t after, int64_t before,
+                                int periodic, const double* wuni_host, int w_uni, int lo, int hi,
+                                double alpha, double beta, pt_stream_t stream) {
+  PT_REQUIRE(W && start && U && Y, "pt_stencil_apply: null pointer");
+  PT_REQUIRE(wmax >= 1 && wmax <= MAXW, "pt_stencil_apply: wmax=%d outside [1,%d]", wmax, MAXW);
+  PT_REQUIRE(n >= 1 && n >= wmax, "pt_stencil_apply: n=%d smaller than the stencil width %d", n, wmax);
+  PT_REQUIRE(after >= 0 && before >= 1, "pt_stencil_apply: bad field shape");
+  PT_REQUIRE(U != Y, "pt_stencil_apply: in-place application is not supported");
+  if (after == 0) return PT_OK;
+  StencilParams p;
+  p.W = W; p.start = start; p.U = U; p.Y = Y;
+  p.wmax = wmax; p.n = n; p.after = after; p.before = before;
+  p.periodic = periodic ? 1 : 0;
+  p.alpha = alpha; p.beta = beta;
+  p.lo = 0; p.hi = 0;
+  cudaStream_t st = pt::as_stream(stream);
+
+  const bool fast = wuni_host != nullptr && (w_uni == 3 || w_uni == 5 || w_uni == 7 || w_uni == 9) &&
+                    lo >= 0 && hi <= n && hi - lo >= 2 * w_uni &&
+                    (periodic || (lo >= w_uni / 2 && hi <= n - w_uni / 2));
+  if (!fast) return launch_table(p, 0, 0, st);  // every row through the table
+
+  UniWeights uw;
+  for (int s = 0; s < MAXW; ++s) uw.w[s] = s < w_uni ? wuni_host[s] : 0.0;
+  p.lo = lo; p.hi = hi;
+  switch (w_uni) {
+    case 3: return launch_fast<3>(p, uw, st);
+    case 5: return launch_fast<5>(p, uw, st);
+    case 7: return launch_fast<7>(p, uw, st);
+    default: return launch_fast<9>(p, uw, st);
+  }
+}
