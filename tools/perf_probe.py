@@ -1,0 +1,81 @@
+"""Kernel-only timings at the BASELINE shapes (CUDA events on torch's current stream).
+Usage: python tools/perf_probe.py [dense|stencil|all]"""
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+import pytristan_b200 as pt
+from pytristan_b200 import _lib
+from pytristan_b200.operators import _DiffMat
+
+PEAK_TF = 37.0
+HBM = 6555.5
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def dense(npts, axis, batch, label):
+    n = npts[axis]
+    D = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    op = _DiffMat._wrap(D, npts, axis, 1, None)
+    P = int(np.prod(npts))
+    U = torch.randn(batch, P, dtype=torch.float64, device="cuda")
+    Y = torch.empty_like(U)
+    op.apply(U, out=Y)
+    ms = timeit(lambda: op.apply(U, out=Y))
+    fl = 2.0 * n * P * batch
+    print(json.dumps({"case": label, "ms": round(ms, 4), "tflops": round(fl / ms * 1e-9, 2),
+                      "frac_fp64_peak": round(fl / ms * 1e-9 / PEAK_TF, 3), "gpts_s": round(P * batch / ms * 1e-6, 2)}))
+
+
+def stencil(npts, axis, batch, label, order=1, acc=6):
+    axes = [np.linspace(0, 1, m) for m in npts]
+    F = pt.FinDiffMat(axes[axis], order=order, accuracy=acc)
+    F.npts, F.axis = tuple(npts), axis
+    P = int(np.prod(npts))
+    U = torch.randn(batch, P, dtype=torch.float64, device="cuda")
+    Y = torch.empty_like(U)
+    F.apply(U, out=Y)
+    ms = timeit(lambda: F.apply(U, out=Y))
+    by = 16.0 * P * batch
+    print(json.dumps({"case": label, "ms": round(ms, 4), "gbs": round(by / ms * 1e-6, 1),
+                      "frac_hbm": round(by / ms * 1e-6 / HBM, 3), "gpts_s": round(P * batch / ms * 1e-6, 2)}))
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("dense", "all"):
+        dense((1024, 257), 0, 64, "cfg2 d/dx K2 n=1024")
+        dense((1024, 257), 1, 64, "cfg2 d2/dy2 K1 n=257")
+        dense((1024, 512), 1, 16, "cfg3 radial K1 n=512")
+        dense((1024, 1024), 1, 8, "cfg3 radial K1 n=1024")
+        dense((8192, 2048), 1, 1, "cfg5a-1/8 K1 n=2048 before=8192")
+        dense((2048, 8192), 0, 1, "K2 n=2048 after=8192")
+        dense((512, 512, 512), 0, 1, "cfg5b x K2 n=512")
+        dense((512, 512, 512), 1, 1, "cfg5b y K1 n=512")
+        dense((512, 512, 512), 2, 1, "cfg5b z K1 n=512")
+        dense((64,), 0, 1, "cfg1 n=64 single field")
+    if what in ("stencil", "all"):
+        stencil((512, 512, 512), 0, 1, "512^3 x (K3)")
+        stencil((512, 512, 512), 1, 1, "512^3 y (K4)")
+        stencil((512, 512, 512), 2, 1, "512^3 z (K4)")
+        stencil((1024, 1024, 512), 0, 1, "1024x1024x512 x (K3)")
+        stencil((1024, 1024, 512), 1, 1, "1024x1024x512 y (K4)")
+        stencil((1024, 1024, 512), 2, 1, "1024x1024x512 z (K4)")
+        x = torch.randn(1 << 28, dtype=torch.float64, device="cuda"); y = torch.empty_like(x)
+        ms = timeit(lambda: y.copy_(x))
+        print(json.dumps({"case": "torch copy 2 GiB", "ms": round(ms, 4), "gbs": round(2 * x.numel() * 8 / ms * 1e-6, 1)}))
