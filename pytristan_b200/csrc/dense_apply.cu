@@ -72,8 +72,69 @@ struct Cfg {
   static constexpr size_t SMEM = size_t(STAGES) * STAGE * sizeof(double);
 };
 
-template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16>
-__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1)
+
+// ---- per-warp compute over one staged k-chunk, specialised on the exact number of m-tiles (MT) the
+// warp owns.  Predicated-off DMMAs still occupy the tensor pipe for their full 16 cycles (measured:
+// ncu r01a), so a warp that owns fewer than WM tiles must branch to code that only issues its own.
+template <class C, int MT, int WMAX, int WN, bool KCONTIG>
+__device__ __forceinline__ void load_frags(const double* As, const double* Bs, int pp, double (&af)[WMAX],
+                                           double (&bf)[WN]) {
+#pragma unroll
+  for (int i = 0; i < MT; ++i) af[i] = As[(pp * C::BM + i * 8) * 4];
+#pragma unroll
+  for (int j = 0; j < WN; ++j) bf[j] = KCONTIG ? Bs[j * 8 * C::PB + pp * 4] : Bs[pp * 4 * C::PB + j * 8];
+}
+
+template <class C, int MT, int WMAX, int WN, int BKP, bool KCONTIG>
+__device__ __forceinline__ void compute_full(const double* As, const double* Bs, double (&acc)[WMAX][WN][2]) {
+  // software pipelined: fragments of panel pp+1 are loaded before the DMMAs of panel pp issue
+  double af[2][WMAX], bf[2][WN];
+  load_frags<C, MT, WMAX, WN, KCONTIG>(As, Bs, 0, af[0], bf[0]);
+#pragma unroll
+  for (int pp = 0; pp < BKP; ++pp) {
+    if (pp + 1 < BKP) load_frags<C, MT, WMAX, WN, KCONTIG>(As, Bs, pp + 1, af[(pp + 1) & 1], bf[(pp + 1) & 1]);
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < WN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[pp & 1][i], bf[pp & 1][j]);
+  }
+}
+
+template <class C, int MT, int WMAX, int WN, bool KCONTIG>
+__device__ __forceinline__ void compute_partial(const double* As, const double* Bs, double (&acc)[WMAX][WN][2],
+                                                int npanels) {
+#pragma unroll 1
+  for (int pp = 0; pp < npanels; ++pp) {
+    double af[WMAX], bf[WN];
+    load_frags<C, MT, WMAX, WN, KCONTIG>(As, Bs, pp, af, bf);
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < WN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+  }
+}
+
+template <class C, int MT, int WMAX, int WN, int BKP, bool KCONTIG>
+struct MtDispatch {
+  static __device__ __forceinline__ void full(int my_mt, const double* As, const double* Bs,
+                                              double (&acc)[WMAX][WN][2]) {
+    if (my_mt == MT) compute_full<C, MT, WMAX, WN, BKP, KCONTIG>(As, Bs, acc);
+    else MtDispatch<C, MT - 1, WMAX, WN, BKP, KCONTIG>::full(my_mt, As, Bs, acc);
+  }
+  static __device__ __forceinline__ void partial(int my_mt, const double* As, const double* Bs,
+                                                 double (&acc)[WMAX][WN][2], int npanels) {
+    if (my_mt == MT) compute_partial<C, MT, WMAX, WN, KCONTIG>(As, Bs, acc, npanels);
+    else MtDispatch<C, MT - 1, WMAX, WN, BKP, KCONTIG>::partial(my_mt, As, Bs, acc, npanels);
+  }
+};
+template <class C, int WMAX, int WN, int BKP, bool KCONTIG>
+struct MtDispatch<C, 0, WMAX, WN, BKP, KCONTIG> {
+  static __device__ __forceinline__ void full(int, const double*, const double*, double (&)[WMAX][WN][2]) {}
+  static __device__ __forceinline__ void partial(int, const double*, const double*, double (&)[WMAX][WN][2], int) {}
+};
+
+template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
 dense_apply_kernel(const DenseParams p) {
   using C = Cfg<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16>;
   extern __shared__ __align__(16) double smem[];
@@ -132,11 +193,11 @@ dense_apply_kernel(const DenseParams p) {
     b_r0 = tid / CPR2;  // first column served
   }
 
-  auto load_stage = [&](int stage, int chunk) {
+  // generic (bounds-checked) loader: used for the chunk that crosses the end of the k range
+  auto load_stage_edge = [&](int stage, int chunk) {
     double* As = smem + size_t(stage) * C::STAGE;
     double* Bs = As + C::A_STAGE;
     const int kp0 = chunk * BKP;
-    // operator tile: BKP panels of rows_blk*4 contiguous doubles
     for (int idx = tid; idx < BKP * C::BM * 2; idx += C::NT) {
       const int pp = idx / (C::BM * 2);
       const int c = idx - pp * (C::BM * 2);
@@ -175,6 +236,59 @@ dense_apply_kernel(const DenseParams p) {
     }
   };
 
+  // fast loader for chunks that lie entirely inside the k range: running pointers, no index
+  // arithmetic in the loop (chunks are always loaded in increasing order).  The loader burst is
+  // what keeps a warp away from the tensor pipe, so it is kept to a few instructions per copy.
+  constexpr int ASUB = (C::BM * 2) / C::NT;  // 16-byte pieces of one operator panel per thread
+  static_assert((C::BM * 2) % C::NT == 0, "operator loader shape");
+  const int64_t a_panel = int64_t(p.MP) * 4;
+  const double* a_ptr = p.Dp + size_t(m0) * 4 + tid * 2;
+  unsigned a_ok = 0;
+#pragma unroll
+  for (int sub = 0; sub < ASUB; ++sub)
+    if (((tid + sub * C::NT) >> 1) < rows_blk) a_ok |= 1u << sub;
+  const double* b_ptr;
+  int64_t b_rstep;
+  unsigned b_ok = 0;
+  if (!KCONTIG) {
+    b_ptr = b_src + int64_t(b_r0) * p.before;
+    b_rstep = int64_t(RPP1) * p.before;
+    b_ok = b_col_ok ? ~0u : 0u;
+  } else {
+    b_ptr = p.U + (n0 + b_r0) * p.n_in + b_cc * EPC;
+    b_rstep = int64_t(RPP2) * p.n_in;
+#pragma unroll
+    for (int r = 0; r < C::BN / RPP2; ++r)
+      if (n0 + b_r0 + r * RPP2 < p.NN) b_ok |= 1u << r;
+  }
+  const int64_t b_cstep = KCONTIG ? int64_t(C::BK) : int64_t(C::BK) * p.before;
+
+  auto load_stage = [&](int stage, int chunk) {
+    if ((chunk + 1) * C::BK > p.n_in) { load_stage_edge(stage, chunk); return; }
+    double* As = smem + size_t(stage) * C::STAGE;
+    double* Bs = As + C::A_STAGE;
+#pragma unroll
+    for (int pp = 0; pp < BKP; ++pp)
+#pragma unroll
+      for (int sub = 0; sub < ASUB; ++sub) {
+        const bool ok = (a_ok >> sub) & 1u;
+        cp_async16(As + pp * C::BM * 4 + (tid + sub * C::NT) * 2,
+                   ok ? a_ptr + pp * a_panel + sub * C::NT * 2 : p.Dp, ok ? 16 : 0);
+      }
+    a_ptr += BKP * a_panel;
+    constexpr int BR = KCONTIG ? C::BN / RPP2 : C::BK / RPP1;
+    constexpr int RPP = KCONTIG ? RPP2 : RPP1;
+#pragma unroll
+    for (int r = 0; r < BR; ++r) {
+      const bool ok = (b_ok >> (KCONTIG ? r : 0)) & 1u;
+      double* dst = Bs + (b_r0 + r * RPP) * C::PB + b_cc * EPC;
+      const double* src = ok ? b_ptr + r * b_rstep : p.U;
+      if (VEC16) cp_async16(dst, src, ok ? 16 : 0);
+      else cp_async8(dst, src, ok ? 8 : 0);
+    }
+    b_ptr += b_cstep;
+  };
+
   double acc[WM][WN][2];
 #pragma unroll
   for (int i = 0; i < WM; ++i)
@@ -188,6 +302,13 @@ dense_apply_kernel(const DenseParams p) {
     cp_async_commit();
   }
 
+  // fragment addressing: A fragment (8 rows x 4 k) = 32 consecutive doubles, lane l reads double l;
+  // B fragment: k = t, column = g
+  const int a_off = my_mt0 * 32 + lane;
+  const int b_off = KCONTIG ? ((wn * WN * 8 + g) * C::PB + t) : (t * C::PB + wn * WN * 8 + g);
+  const int nfull = p.KP / BKP;       // chunks whose BKP panels are all valid
+  const int tail = p.KP - nfull * BKP;
+
   // ---- main loop ----------------------------------------------------------------------------
   for (int kc = 0; kc < nchunks; ++kc) {
     cp_async_wait<STAGES - 2>();
@@ -197,29 +318,10 @@ dense_apply_kernel(const DenseParams p) {
       if (nxt < nchunks) load_stage(nxt % STAGES, nxt);
       cp_async_commit();
     }
-    const double* As = smem + size_t(kc % STAGES) * C::STAGE;
-    const double* Bs = As + C::A_STAGE;
-    const int kp0 = kc * BKP;
-#pragma unroll
-    for (int pp = 0; pp < BKP; ++pp) {
-      if (kp0 + pp < p.KP) {
-        double af[WM], bf[WN];
-#pragma unroll
-        for (int i = 0; i < WM; ++i)
-          if (i < my_mt) af[i] = As[(pp * C::BM + (my_mt0 + i) * 8) * 4 + lane];
-#pragma unroll
-        for (int j = 0; j < WN; ++j) {
-          const int col = (wn * WN + j) * 8 + g;
-          bf[j] = KCONTIG ? Bs[col * C::PB + pp * 4 + t] : Bs[(pp * 4 + t) * C::PB + col];
-        }
-#pragma unroll
-        for (int i = 0; i < WM; ++i)
-          if (i < my_mt) {
-#pragma unroll
-            for (int j = 0; j < WN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-          }
-      }
-    }
+    const double* As = smem + size_t(kc % STAGES) * C::STAGE + a_off;
+    const double* Bs = smem + size_t(kc % STAGES) * C::STAGE + C::A_STAGE + b_off;
+    if (kc < nfull) MtDispatch<C, WM, WM, WN, BKP, KCONTIG>::full(my_mt, As, Bs, acc);
+    else MtDispatch<C, WM, WM, WN, BKP, KCONTIG>::partial(my_mt, As, Bs, acc, tail);
   }
   cp_async_wait<0>();
 
@@ -289,10 +391,10 @@ __global__ void pack_operator_kernel(const double* __restrict__ D, int n_out, in
   }
 }
 
-template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16>
+template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB = 1>
 int launch_cfg(DenseParams& p, cudaStream_t stream) {
   using C = Cfg<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16>;
-  auto kern = dense_apply_kernel<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16>;
+  auto kern = dense_apply_kernel<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16, MINB>;
   static bool attr_set[64] = {false};
   int dev = 0;
   PT_CUDA(cudaGetDevice(&dev));
@@ -313,15 +415,26 @@ int launch_cfg(DenseParams& p, cudaStream_t stream) {
   return pt::check_launch("pt_dense_apply");
 }
 
+int g_dense_config = 5;  // tuning hook (pt_debug_set_dense_config); 5 = default
+
 template <bool KCONTIG, bool VEC16>
 int launch_shape(DenseParams& p, cudaStream_t stream) {
-  // one configuration for now: 8 warps, 128x128 CTA tile (64x32 per warp), BK = 16, 4 stages
-  return launch_cfg<2, 4, 8, 4, 4, 4, KCONTIG, VEC16>(p, stream);
+  switch (g_dense_config) {
+    case 2: return launch_cfg<2, 4, 8, 4, 8, 3, KCONTIG, VEC16>(p, stream);   // BK = 32, 3 stages
+    case 6: return launch_cfg<2, 2, 8, 4, 8, 2, KCONTIG, VEC16, 2>(p, stream);  // same, BK = 32, 2 stages
+    case 0: return launch_cfg<2, 4, 8, 4, 4, 4, KCONTIG, VEC16>(p, stream);  // 8 warps, 64x32 per warp
+    default: return launch_cfg<2, 2, 8, 4, 4, 4, KCONTIG, VEC16, 2>(p, stream);
+  }
 }
 
 inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
 
 }  // namespace
+
+extern "C" int pt_debug_set_dense_config(int id) {
+  g_dense_config = id;
+  return PT_OK;
+}
 
 extern "C" int64_t pt_packed_size(int n_out, int n_in) {
   if (n_out <= 0 || n_in <= 0) return 0;
