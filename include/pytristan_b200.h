@@ -120,6 +120,15 @@ int pt_stencil_apply(const double* W, const int32_t* start, int wmax, int n, con
                      const double* wuni_host, int w_uni, int lo, int hi, double alpha,
                      double beta, pt_stream_t stream);
 
+/* Rectangular variant for slab-sharded axes (multi-GPU): U holds n_in rows per slab (the local
+ * rows plus halo planes), Y holds n_out rows; output row i corresponds to input row i + shift,
+ * start[i] (one entry per OUTPUT row) is relative to the input slab, and canonical rows
+ * lo <= i < hi read input rows i + shift - floor(w_uni/2) ... i + shift + floor(w_uni/2). */
+int pt_stencil_apply_ex(const double* W, const int32_t* start, int wmax, int n_in, int n_out,
+                        int shift, const double* U, double* Y, int64_t after, int64_t before,
+                        int periodic, const double* wuni_host, int w_uni, int lo, int hi,
+                        double alpha, double beta, pt_stream_t stream);
+
 /* ---- K7: pencil-transpose pack/unpack (multi-GPU) ----------------------------------------- */
 /* Generic 3-D permutation copy used on both sides of the all-to-all: in is (d2, d1, d0)
  * C-contiguous; out[perm] = in, perm one of the 6 axis orders encoded as p0 + 3*p1 + 9*p2

@@ -40,6 +40,9 @@ SIGNATURES = {
     "pt_stencil_apply": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64,
                                   _c_i32, ctypes.POINTER(_c_f64), _c_i32, _c_i32, _c_i32, _c_f64,
                                   _c_f64, _c_ptr]),
+    "pt_stencil_apply_ex": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64,
+                                     _c_i64, _c_i32, ctypes.POINTER(_c_f64), _c_i32, _c_i32, _c_i32,
+                                     _c_f64, _c_f64, _c_ptr]),
     "pt_permute3d": (_c_i32, [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_i64, _c_i32, _c_ptr]),
     "pt_measure_dmma_peak": (_c_i32, [ctypes.POINTER(_c_f64), _c_i32]),
 }

@@ -28,7 +28,8 @@ struct StencilParams {
   const int32_t* __restrict__ start;
   const double* __restrict__ U;
   double* __restrict__ Y;
-  int wmax, n;
+  int wmax, n;       // n = rows of U per slab (wrap/bounds)
+  int n_out, shift;  // rows of Y per slab; output row i sits at input row i + shift
   int64_t after, before;
   int periodic;
   int lo, hi;  // canonical interior rows [lo, hi) (fast kernels); table rows elsewhere
@@ -60,11 +61,11 @@ __device__ __forceinline__ void store_point(const StencilParams& p, double* y, d
 }
 
 // ---- generic table kernel ------------------------------------------------------------------------
-// rows r = a*n + i in [row_lo, row_hi) restricted to i outside [skip_lo, skip_hi)
+// output rows i outside [skip_lo, skip_hi) of every slab; start[i] is relative to the input slab
 __global__ void __launch_bounds__(256) stencil_table_kernel(const StencilParams p, int skip_lo,
                                                              int skip_hi) {
   // rows that need the table per slab: i in [0, skip_lo) U [skip_hi, n)
-  const int per_slab = skip_lo + (p.n - skip_hi);
+  const int per_slab = skip_lo + (p.n_out - skip_hi);
   const int64_t total = p.after * int64_t(per_slab) * p.before;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(256) stencil_table_kernel(const StencilParams 
     const int i = ii < skip_lo ? ii : ii - skip_lo + skip_hi;
     const double* base = p.U + a * int64_t(p.n) * p.before + b;
     const double v = table_point(p, base, i);
-    store_point(p, p.Y + (a * int64_t(p.n) + i) * p.before + b, v);
+    store_point(p, p.Y + (a * int64_t(p.n_out) + i) * p.before + b, v);
   }
 }
 
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(128) stencil_strided_kernel(const StencilParam
   const int64_t a = blockIdx.z;
   const int64_t stride = p.before / V;  // row stride in vectors
   const T* __restrict__ u = reinterpret_cast<const T*>(p.U + a * int64_t(p.n) * p.before) + colv;
-  T* __restrict__ y = reinterpret_cast<T*>(p.Y + a * int64_t(p.n) * p.before) + colv;
+  T* __restrict__ y = reinterpret_cast<T*>(p.Y + a * int64_t(p.n_out) * p.before) + colv;
   const int c0 = p.lo + blockIdx.y * ichunk;
   const int c1 = min(c0 + ichunk, p.hi);
   if (c0 >= c1) return;
@@ -132,13 +133,13 @@ __global__ void __launch_bounds__(128) stencil_strided_kernel(const StencilParam
 
   T v[2 * W - 1];
 #pragma unroll
-  for (int s = 0; s < W - 1; ++s) v[s] = row(c0 - HW + s);
+  for (int s = 0; s < W - 1; ++s) v[s] = row(c0 + p.shift - HW + s);
 
   for (int i = c0; i < c1; i += W) {
     // W independent loads in flight per thread
 #pragma unroll
     for (int q = 0; q < W; ++q) {
-      const int j = i + q + HW;
+      const int j = i + q + p.shift + HW;
       if (i + q < c1) v[W - 1 + q] = row(j);
     }
 #pragma unroll
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(256) stencil_contig_kernel(const StencilParams
     const int c = (idx - r * cpr) * V;      // offset inside the padded row
     const int64_t a = row0 + r;
     if (a >= p.after) continue;
-    int j = i0 - HL + c;                     // global index of the first double of the chunk
+    int j = i0 + p.shift - HL + c;           // input index of the first double of the chunk
     const double* rowp = p.U + a * int64_t(n);
     double* dst = sm + r * pitch + c;
     if (V == 2) {
@@ -218,8 +219,8 @@ __global__ void __launch_bounds__(256) stencil_contig_kernel(const StencilParams
     const int li = (idx - r * ipr) * 2;   // local point index (even)
     const int64_t a = row0 + r;
     const int i = i0 + li;
-    if (a >= p.after || i >= n) continue;
-    const double* s = sm + r * pitch + li;  // s[0] is point i - HL
+    if (a >= p.after || i >= p.n_out) continue;
+    const double* s = sm + r * pitch + li;  // s[0] is input point i + shift - HL
     double v[10];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256) stencil_contig_kernel(const StencilParams
       acc0 = fma(w[q], v[HL - HW + q], acc0);
       acc1 = fma(w[q], v[HL - HW + 1 + q], acc1);
     }
-    double* yp = p.Y + a * int64_t(n) + i;
+    double* yp = p.Y + a * int64_t(p.n_out) + i;
     const bool ok0 = (i >= p.lo && i < p.hi);
     const bool ok1 = (i + 1 >= p.lo && i + 1 < p.hi);  // i + 1 < n implied by hi <= n
     if (V == 2 && ok0 && ok1) {
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(256) stencil_contig_kernel(const StencilParams
 inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
 
 int launch_table(const StencilParams& p, int skip_lo, int skip_hi, cudaStream_t st) {
-  const int per_slab = skip_lo + (p.n - skip_hi);
+  const int per_slab = skip_lo + (p.n_out - skip_hi);
   const int64_t total = p.after * int64_t(per_slab) * p.before;
   if (total <= 0) return PT_OK;
   int64_t blocks = (total + 255) / 256;
@@ -283,7 +284,7 @@ int launch_strided(const StencilParams& p, const UniWeights& uw, cudaStream_t st
     StencilParams q = p;
     const int64_t na = (p.after - a0 < 65535) ? p.after - a0 : 65535;
     q.U = p.U + a0 * int64_t(p.n) * p.before;
-    q.Y = p.Y + a0 * int64_t(p.n) * p.before;
+    q.Y = p.Y + a0 * int64_t(p.n_out) * p.before;
     q.after = na;
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)na);
     if (vec) stencil_strided_kernel<W, 2><<<grid, 128, 0, st>>>(q, uw, ichunk, ncolv);
@@ -296,15 +297,15 @@ int launch_strided(const StencilParams& p, const UniWeights& uw, cudaStream_t st
 
 template <int W>
 int launch_contig(const StencilParams& p, const UniWeights& uw, cudaStream_t st) {
-  const bool vec = (p.n % 2 == 0) && aligned16(p.U) && aligned16(p.Y);
+  const bool vec = (p.n % 2 == 0) && (p.n_out % 2 == 0) && (p.shift % 2 == 0) && aligned16(p.U) && aligned16(p.Y);
   // tile: TI points per row segment (even), ROWS rows, about 4096 points per block
-  int TI = p.n + (p.n & 1);
+  int TI = p.n_out + (p.n_out & 1);
   if (TI > 2048) TI = 2048;
   int ROWS = 4096 / TI;
   if (ROWS > 5120 / (TI + 8)) ROWS = 5120 / (TI + 8);  // keep the tile under 40 KB of smem
   if (ROWS < 1) ROWS = 1;
   if (ROWS > p.after) ROWS = int(p.after);
-  const int tiles_per_row = (p.n + TI - 1) / TI;
+  const int tiles_per_row = (p.n_out + TI - 1) / TI;
   const int64_t tiles = ((p.after + ROWS - 1) / ROWS) * tiles_per_row;
   PT_REQUIRE(tiles <= 2147483647LL, "pt_stencil_apply: grid too large");
   const size_t smem = size_t(ROWS) * (TI + 8) * sizeof(double);
@@ -322,27 +323,31 @@ int launch_fast(const StencilParams& p, const UniWeights& uw, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" int pt_stencil_apply(const double* W, const int32_t* start, int wmax, int n,
-                                const double* U, double* Y, int64_t after, int64_t before,
-                                int periodic, const double* wuni_host, int w_uni, int lo, int hi,
-                                double alpha, double beta, pt_stream_t stream) {
+extern "C" int pt_stencil_apply_ex(const double* W, const int32_t* start, int wmax, int n_in, int n_out,
+                                   int shift, const double* U, double* Y, int64_t after, int64_t before,
+                                   int periodic, const double* wuni_host, int w_uni, int lo, int hi,
+                                   double alpha, double beta, pt_stream_t stream) {
   PT_REQUIRE(W && start && U && Y, "pt_stencil_apply: null pointer");
   PT_REQUIRE(wmax >= 1 && wmax <= MAXW, "pt_stencil_apply: wmax=%d outside [1,%d]", wmax, MAXW);
-  PT_REQUIRE(n >= 1 && n >= wmax, "pt_stencil_apply: n=%d smaller than the stencil width %d", n, wmax);
+  PT_REQUIRE(n_in >= 1 && n_in >= wmax, "pt_stencil_apply: n=%d smaller than the stencil width %d", n_in, wmax);
+  PT_REQUIRE(n_out >= 0 && shift >= 0 && shift + n_out <= n_in, "pt_stencil_apply: output rows [%d, %d) outside the input rows [0, %d)", shift, shift + n_out, n_in);
+  PT_REQUIRE(!periodic || (n_out == n_in && shift == 0), "pt_stencil_apply: periodic wrap needs the whole axis");
   PT_REQUIRE(after >= 0 && before >= 1, "pt_stencil_apply: bad field shape");
   PT_REQUIRE(U != Y, "pt_stencil_apply: in-place application is not supported");
-  if (after == 0) return PT_OK;
+  if (after == 0 || n_out == 0) return PT_OK;
   StencilParams p;
   p.W = W; p.start = start; p.U = U; p.Y = Y;
-  p.wmax = wmax; p.n = n; p.after = after; p.before = before;
+  p.wmax = wmax; p.n = n_in; p.n_out = n_out; p.shift = shift; p.after = after; p.before = before;
   p.periodic = periodic ? 1 : 0;
   p.alpha = alpha; p.beta = beta;
   p.lo = 0; p.hi = 0;
   cudaStream_t st = pt::as_stream(stream);
 
+  // canonical rows must read inside the input slab: i + shift - hw >= 0 and i + shift + hw < n_in
+  const int hwu = w_uni / 2;
   const bool fast = wuni_host != nullptr && (w_uni == 3 || w_uni == 5 || w_uni == 7 || w_uni == 9) &&
-                    lo >= 0 && hi <= n && hi - lo >= 2 * w_uni &&
-                    (periodic || (lo >= w_uni / 2 && hi <= n - w_uni / 2));
+                    lo >= 0 && hi <= n_out && hi - lo >= 2 * w_uni &&
+                    (periodic || (lo + shift >= hwu && hi + shift <= n_in - hwu));
   if (!fast) return launch_table(p, 0, 0, st);  // every row through the table
 
   UniWeights uw;
@@ -354,4 +359,12 @@ extern "C" int pt_stencil_apply(const double* W, const int32_t* start, int wmax,
     case 7: return launch_fast<7>(p, uw, st);
     default: return launch_fast<9>(p, uw, st);
   }
+}
+
+extern "C" int pt_stencil_apply(const double* W, const int32_t* start, int wmax, int n,
+                                const double* U, double* Y, int64_t after, int64_t before,
+                                int periodic, const double* wuni_host, int w_uni, int lo, int hi,
+                                double alpha, double beta, pt_stream_t stream) {
+  return pt_stencil_apply_ex(W, start, wmax, n, n, 0, U, Y, after, before, periodic, wuni_host, w_uni, lo,
+                             hi, alpha, beta, stream);
 }

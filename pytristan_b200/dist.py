@@ -1,0 +1,304 @@
+"""Multi-GPU partitioning of the hot path over one NVSwitch box (one process per GPU,
+``torch.distributed`` for the plumbing).
+
+* ``shard_range``        — fields / non-differentiated axes split contiguously, **no communication**.
+* ``SlabStencil``        — a ``FinDiffMat`` along the slab-sharded (slowest) grid axis: halo planes are
+                           exchanged with the two neighbours (NCCL send/recv straight out of / into the
+                           extended field buffer — planes of the slowest axis are contiguous, nothing is
+                           packed), then the rectangular stencil kernel (``pt_stencil_apply_ex``) runs on
+                           the local rows; boundary slabs keep the one-sided closures.
+* ``PencilTranspose``    — 2-D (py x pz) pencil decomposition of a 3-D field; the x<->y and y<->z
+                           redistributions are pack (``pt_permute3d``, fastest axis untouched) ->
+                           ``all_to_all_single`` -> unpack.  Because the apply kernels address any axis
+                           in place, a "transpose" only redistributes; no local axis permutation that
+                           moves the fastest axis is ever needed.
+* ``pencil_apply_sum``   — sum of one operator per axis (e.g. a 3-D Chebyshev Laplacian) on pencils.
+
+The two module-level functions ``_permute3d`` and ``_stencil_local`` are the only places that touch
+the GPU library; the world-size-2 gloo tests replace them with CPU doubles to exercise the
+bookkeeping and the collectives without a GPU.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["shard_range", "SlabStencil", "PencilTranspose", "pencil_apply_sum"]
+
+
+def shard_range(total, rank, world):
+    """Contiguous balanced split of ``total`` items: returns ``(lo, hi)`` of ``rank``."""
+    base, rem = divmod(int(total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+# ---- the two device entry points (replaced by CPU doubles in the gloo tests) -------------------
+def _permute3d(src, dst, d2, d1, d0, perm):
+    """dst = src viewed as (d2, d1, d0) with axes reordered to ``perm`` (slowest first)."""
+    lib = _lib.load()
+    code = perm[0] + 3 * perm[1] + 9 * perm[2]
+    _lib.check(lib.pt_permute3d(_lib.dptr(src), _lib.dptr(dst), d2, d1, d0, code, _lib.stream_ptr()),
+               "pt_permute3d")
+
+
+def _stencil_local(band, ext, out, n_in, n_out, shift, after, before, alpha, beta):
+    lib = _lib.load()
+    if band["wuni"] is not None:
+        wuni = (ctypes.c_double * band["w"])(*band["wuni"].tolist())
+        w_uni = band["w"]
+    else:
+        wuni, w_uni = None, 0
+    _lib.check(
+        lib.pt_stencil_apply_ex(_lib.dptr(band["d_w"]), _lib.dptr(band["d_start"]), band["wmax"], n_in,
+                                n_out, shift, _lib.dptr(ext), _lib.dptr(out), after, before, 0, wuni, w_uni,
+                                band["lo"], band["hi"], float(alpha), float(beta), _lib.stream_ptr()),
+        "pt_stencil_apply_ex",
+    )
+
+
+# ---- slab-sharded stencil --------------------------------------------------------------------------
+class SlabStencil:
+    """``FinDiffMat`` along the slowest grid axis when that axis is split into contiguous slabs.
+
+    ``plan = SlabStencil(start, weights, meta, rank, world)`` is built from the *global* band of
+    the operator (``FinDiffMat.start`` / ``.weights``).  The rank owns rows ``[z0, z1)``; its
+    extended buffer has ``halo_lo + (z1 - z0) + halo_hi`` rows.  ``exchange`` fills the halo rows
+    from the neighbours, ``apply`` differentiates the local rows.
+    """
+
+    def __init__(self, start, weights, rank, world, periodic=False, wuni=None, w=None, lo=0, hi=0,
+                 group=None, device=True):
+        start = np.asarray(start, dtype=np.int64)
+        n, wmax = weights.shape
+        self.n, self.wmax, self.rank, self.world, self.group = n, wmax, rank, world, group
+        self.periodic = bool(periodic)
+        self.z0, self.z1 = shard_range(n, rank, world)
+        self.nloc = self.z1 - self.z0
+        if self.nloc <= 0:
+            raise ValueError("SlabStencil: more ranks than rows")
+        first = start[self.z0:self.z1]
+        self.halo_lo = int(max(0, self.z0 - first.min()))
+        self.halo_hi = int(max(0, (first.max() + wmax) - self.z1))
+        if not self.periodic:
+            self.halo_lo = min(self.halo_lo, self.z0)
+            self.halo_hi = min(self.halo_hi, n - self.z1)
+        # what the neighbours need from this rank (their halos), computed from the same band
+        self.send_lo = self._neighbour_need(start, rank - 1, upper=True)    # rows sent to rank-1
+        self.send_hi = self._neighbour_need(start, rank + 1, upper=False)   # rows sent to rank+1
+        def rows_of(r):
+            lo_r, hi_r = shard_range(n, r % world, world)
+            return hi_r - lo_r
+
+        if (max(self.send_lo, self.send_hi) > self.nloc or self.halo_lo > rows_of(rank - 1)
+                or self.halo_hi > rows_of(rank + 1)):
+            raise ValueError("SlabStencil: slabs are thinner than the stencil halo")
+        self.n_ext = self.halo_lo + self.nloc + self.halo_hi
+        self.shift = self.halo_lo
+        origin = self.z0 - self.halo_lo                       # global row of ext row 0
+        start_local = (first - origin).astype(np.int32)
+        w_local = np.ascontiguousarray(weights[self.z0:self.z1])
+        hwu = (w // 2) if w else 0
+        if wuni is not None:
+            lo_l = max(lo, self.z0) - self.z0
+            hi_l = min(hi, self.z1) - self.z0
+            if self.periodic:
+                lo_l, hi_l = 0, self.nloc
+        else:
+            lo_l = hi_l = 0
+        self.band = dict(wmax=wmax, w=w or 0, wuni=None if wuni is None else np.asarray(wuni, dtype=np.float64),
+                         lo=int(lo_l), hi=int(max(hi_l, lo_l)), start=start_local, weights=w_local, hw=hwu)
+        if device:
+            torch = _lib.require_cuda()
+            self.band["d_start"] = torch.from_numpy(start_local).cuda()
+            self.band["d_w"] = torch.from_numpy(w_local).cuda()
+
+    @classmethod
+    def from_operator(cls, op, rank, world, group=None):
+        """Plan for a ``FinDiffMat`` bound to the slowest axis of its grid."""
+        band = op._band
+        return cls(band["start"], band["weights"], rank, world, periodic=band["periodic"], wuni=band["wuni"],
+                   w=band["w"], lo=band["lo"], hi=band["hi"], group=group)
+
+    def _neighbour_need(self, start, r, upper):
+        if self.periodic:
+            r %= self.world
+        elif r < 0 or r >= self.world:
+            return 0
+        if r == self.rank and self.world == 1:
+            # single rank, periodic: the halo wraps onto itself
+            pass
+        z0, z1 = shard_range(self.n, r, self.world)
+        first = start[z0:z1]
+        if upper:   # rank r sits below: it needs rows above its z1, i.e. this rank's first rows
+            need = int(max(0, (first.max() + self.wmax) - z1))
+            return need if self.periodic else min(need, self.n - z1)
+        need = int(max(0, z0 - first.min()))
+        return need if self.periodic else min(need, z0)
+
+    # -- buffers -----------------------------------------------------------------------------------
+    def ext_shape(self, nfields, plane):
+        return (nfields, self.n_ext, plane)
+
+    def interior(self, ext):
+        """View of the rank's own rows inside an extended buffer ``(nfields, n_ext, plane)``."""
+        return ext[:, self.halo_lo:self.halo_lo + self.nloc, :]
+
+    def exchange(self, ext):
+        """Fill the halo rows of ``ext`` from the neighbouring ranks (grouped send/recv)."""
+        import torch.distributed as dist
+
+        if self.world == 1:
+            if self.periodic:
+                if self.halo_lo:
+                    ext[:, :self.halo_lo] = ext[:, self.halo_lo + self.nloc - self.halo_lo:self.halo_lo + self.nloc]
+                if self.halo_hi:
+                    ext[:, self.halo_lo + self.nloc:] = ext[:, self.halo_lo:self.halo_lo + self.halo_hi]
+            return
+        ops, keep = [], []
+        lo_peer, hi_peer = self.rank - 1, self.rank + 1
+        if self.periodic:
+            lo_peer %= self.world
+            hi_peer %= self.world
+        nf = ext.shape[0]
+        for f in range(nf):       # one contiguous block per field
+            own = ext[f, self.halo_lo:self.halo_lo + self.nloc]
+            if self.send_lo and 0 <= lo_peer < self.world:
+                ops.append(dist.P2POp(dist.isend, own[:self.send_lo], self._global(lo_peer), self.group))
+            if self.send_hi and 0 <= hi_peer < self.world:
+                ops.append(dist.P2POp(dist.isend, own[self.nloc - self.send_hi:], self._global(hi_peer), self.group))
+            # receives are posted upper halo first: with two ranks and a periodic axis both
+            # neighbours are the same peer, and messages between a pair match in posting order
+            # (the peer sends its first rows, which are this rank's upper halo, first)
+            if self.halo_hi and 0 <= hi_peer < self.world:
+                ops.append(dist.P2POp(dist.irecv, ext[f, self.halo_lo + self.nloc:], self._global(hi_peer), self.group))
+            if self.halo_lo and 0 <= lo_peer < self.world:
+                ops.append(dist.P2POp(dist.irecv, ext[f, :self.halo_lo], self._global(lo_peer), self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def _global(self, r):
+        import torch.distributed as dist
+
+        return r if self.group is None else dist.get_global_rank(self.group, r)
+
+    def apply(self, ext, out=None, alpha=1.0, beta=0.0):
+        """Differentiate the local rows of ``ext`` (halos must be current) into ``out``
+        ``(nfields, nloc, plane)``."""
+        nf, n_ext, plane = ext.shape
+        if n_ext != self.n_ext:
+            raise ValueError("SlabStencil.apply: buffer does not have n_ext rows")
+        if out is None:
+            out = ext.new_empty((nf, self.nloc, plane))
+        _stencil_local(self.band, ext, out, self.n_ext, self.nloc, self.shift, nf, plane, alpha, beta)
+        return out
+
+
+# ---- pencil decomposition -----------------------------------------------------------------------------
+class PencilTranspose:
+    """Redistributions of a 3-D field ``(nz, ny, nx)`` (x fastest) over a ``py x pz`` process grid.
+
+    Layout A: ``(nz/pz, ny/py, nx)``   — x local            (rank = rz*py + ry)
+    Layout B: ``(nz/pz, ny, nx/py)``   — y local
+    Layout C: ``(nz, ny/pz, nx/py)``   — z local
+    Leading batch dimensions are allowed (they ride along).
+    """
+
+    def __init__(self, shape, py, pz, rank=None, world=None, groups=None):
+        import torch.distributed as dist
+
+        self.nz, self.ny, self.nx = (int(v) for v in shape)
+        self.py, self.pz = int(py), int(pz)
+        self.world = dist.get_world_size() if world is None else world
+        self.rank = dist.get_rank() if rank is None else rank
+        if self.py * self.pz != self.world:
+            raise ValueError("PencilTranspose: py*pz must equal the world size")
+        for a, b, what in ((self.nx, self.py, "nx % py"), (self.ny, self.py, "ny % py"),
+                           (self.ny, self.pz, "ny % pz"), (self.nz, self.pz, "nz % pz")):
+            if a % b:
+                raise ValueError(f"PencilTranspose: {what} must be 0")
+        self.ry, self.rz = self.rank % self.py, self.rank // self.py
+        self.nzl, self.nyl, self.nxl, self.nyl2 = self.nz // self.pz, self.ny // self.py, self.nx // self.py, self.ny // self.pz
+        if groups is None:
+            rows = [dist.new_group([z * self.py + y for y in range(self.py)]) for z in range(self.pz)]
+            cols = [dist.new_group([z * self.py + y for z in range(self.pz)]) for y in range(self.py)]
+            groups = (rows[self.rz], cols[self.ry])
+        self.row_group, self.col_group = groups
+
+    @staticmethod
+    def _a2a(recv, send, group):
+        import torch.distributed as dist
+
+        dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
+
+    def _swap01(self, t, d2, d1, d0):
+        out = t.new_empty(t.numel())
+        _permute3d(t.reshape(-1), out, d2, d1, d0, (1, 0, 2))
+        return out
+
+    def x_to_y(self, t):
+        """Layout A -> B."""
+        lead = t.numel() // (self.nyl * self.nx)          # batch * nzl
+        send = self._swap01(t, lead * self.nyl, self.py, self.nxl)       # (py, lead*nyl, nxl)
+        recv = send.new_empty(send.numel())
+        self._a2a(recv, send, self.row_group)                             # (py[src], lead, nyl*nxl)
+        out = self._swap01(recv, self.py, lead, self.nyl * self.nxl)     # (lead, py*nyl, nxl)
+        return out.view(*t.shape[:-3], self.nzl, self.ny, self.nxl)
+
+    def y_to_x(self, t):
+        """Layout B -> A."""
+        lead = t.numel() // (self.ny * self.nxl)
+        send = self._swap01(t, lead, self.py, self.nyl * self.nxl)       # (py, lead, nyl*nxl)
+        recv = send.new_empty(send.numel())
+        self._a2a(recv, send, self.row_group)                             # (py[src x-chunk], lead*nyl, nxl)
+        out = self._swap01(recv, self.py, lead * self.nyl, self.nxl)     # (lead*nyl, py, nxl)
+        return out.view(*t.shape[:-3], self.nzl, self.nyl, self.nx)
+
+    def y_to_z(self, t):
+        """Layout B -> C."""
+        batch = t.numel() // (self.nzl * self.ny * self.nxl)
+        blk = self.nyl2 * self.nxl
+        send = self._swap01(t, batch * self.nzl, self.pz, blk)           # (pz, batch*nzl, blk)
+        recv = send.new_empty(send.numel())
+        self._a2a(recv, send, self.col_group)                             # (pz[src], batch, nzl*blk)
+        out = recv if batch == 1 else self._swap01(recv, self.pz, batch, self.nzl * blk)
+        return out.view(*t.shape[:-3], self.nz, self.nyl2, self.nxl)
+
+    def z_to_y(self, t):
+        """Layout C -> B."""
+        batch = t.numel() // (self.nz * self.nyl2 * self.nxl)
+        blk = self.nyl2 * self.nxl
+        send = t.reshape(-1) if batch == 1 else self._swap01(t, batch, self.pz, self.nzl * blk)  # (pz, batch, nzl*blk)
+        recv = send.new_empty(send.numel())
+        self._a2a(recv, send.contiguous(), self.col_group)                # (pz[src y-chunk], batch*nzl, blk)
+        out = self._swap01(recv, self.pz, batch * self.nzl, blk)         # (batch*nzl, pz, blk)
+        return out.view(*t.shape[:-3], self.nzl, self.ny, self.nxl)
+
+
+def pencil_apply_sum(ops, u, pencils, back=False):
+    """``sum_k ops[k] applied along axis k`` of a 3-D field distributed in layout A.
+
+    ``ops = (Dx, Dy, Dz)`` dense operators (any may be None); ``u`` is the local block in layout A
+    ``(nz/pz, ny/py, nx)``.  Returns the result in layout C, or in layout A if ``back``.
+    Two all-to-all rounds carry (u, partial sum) together; each partial sum is accumulated in place
+    by the kernels' fused ``beta = 1`` epilogue.
+    """
+    import torch
+
+    pt = pencils
+    dx, dy, dz = ops
+    acc = torch.zeros_like(u) if dx is None else dx._apply_device(
+        u.reshape(-1), pt.nzl * pt.nyl, pt.nx, 1, None, 1.0, 0.0, None, None).view(u.shape)
+    pair = torch.stack([u, acc])                                   # (2, nzl, nyl, nx)
+    pair = pt.x_to_y(pair)                                         # (2, nzl, ny, nxl)
+    if dy is not None:
+        dy._apply_device(pair[0].reshape(-1), pt.nzl, pt.ny, pt.nxl, pair[1].reshape(-1), 1.0, 1.0, None, None)
+    pair = pt.y_to_z(pair)                                         # (2, nz, nyl2, nxl)
+    if dz is not None:
+        dz._apply_device(pair[0].reshape(-1), 1, pt.nz, pt.nyl2 * pt.nxl, pair[1].reshape(-1), 1.0, 1.0, None, None)
+    res = pair[1]
+    if back:
+        res = pt.y_to_x(pt.z_to_y(res.contiguous()))
+    return res
