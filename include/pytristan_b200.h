@@ -111,14 +111,25 @@ int pt_dense_apply(const double* packed, int n_out, int n_in, const double* U, d
                    const double* scale, int scale_mode, int64_t scale_len, pt_stream_t stream);
 
 /* ---- K3/K4: banded (finite-difference) application --------------------------------------- */
+/* Optional description of the uniform part of a band (all pointers are HOST pointers).  Rows
+ * lo <= i < hi are canonical interior rows: their weights are the w_uni (3, 5, 7 or 9) entries of
+ * wuni applied at offset i - floor(w_uni/2); the kernels keep them in registers.  The remaining
+ * n_bnd = lo + (n_out - hi) boundary rows (top rows first, then bottom rows) may be described by
+ * w_bnd (n_bnd * wmax weights) and start_bnd (n_bnd first columns): with n_bnd <= 8 the
+ * contiguous-axis kernel then computes them out of the same shared-memory tile (single launch). */
+typedef struct pt_uniform_rows {
+  int w_uni, lo, hi, n_bnd;
+  const double* wuni;
+  const double* w_bnd;
+  const int32_t* start_bnd;
+} pt_uniform_rows;
+
 /* Y[a,i,b] = alpha * sum_s W[i*wmax+s] * U[a, start[i]+s, b] + beta * Y[a,i,b].
- * If wuni != NULL, rows lo <= i < hi are canonical interior rows: their weights are the
- * w_uni entries of wuni (HOST pointer, w_uni <= 16) applied at offset i - floor(w_uni/2);
- * the kernels then keep those weights in registers.  periodic != 0 wraps indices modulo n. */
+ * uni may be NULL (every row goes through the per-row table: mapped, non-uniform axes).
+ * periodic != 0 wraps indices modulo n. */
 int pt_stencil_apply(const double* W, const int32_t* start, int wmax, int n, const double* U,
                      double* Y, int64_t after, int64_t before, int periodic,
-                     const double* wuni_host, int w_uni, int lo, int hi, double alpha,
-                     double beta, pt_stream_t stream);
+                     const pt_uniform_rows* uni, double alpha, double beta, pt_stream_t stream);
 
 /* Rectangular variant for slab-sharded axes (multi-GPU): U holds n_in rows per slab (the local
  * rows plus halo planes), Y holds n_out rows; output row i corresponds to input row i + shift,
@@ -126,8 +137,8 @@ int pt_stencil_apply(const double* W, const int32_t* start, int wmax, int n, con
  * lo <= i < hi read input rows i + shift - floor(w_uni/2) ... i + shift + floor(w_uni/2). */
 int pt_stencil_apply_ex(const double* W, const int32_t* start, int wmax, int n_in, int n_out,
                         int shift, const double* U, double* Y, int64_t after, int64_t before,
-                        int periodic, const double* wuni_host, int w_uni, int lo, int hi,
-                        double alpha, double beta, pt_stream_t stream);
+                        int periodic, const pt_uniform_rows* uni, double alpha, double beta,
+                        pt_stream_t stream);
 
 /* ---- K7: pencil-transpose pack/unpack (multi-GPU) ----------------------------------------- */
 /* Generic 3-D permutation copy used on both sides of the all-to-all: in is (d2, d1, d0)

@@ -17,6 +17,37 @@ _c_i64 = ctypes.c_int64
 _c_f64 = ctypes.c_double
 _c_ptr = ctypes.c_void_p
 
+
+
+class UniformRows(ctypes.Structure):
+    """struct pt_uniform_rows (include/pytristan_b200.h)."""
+
+    _fields_ = [("w_uni", _c_i32), ("lo", _c_i32), ("hi", _c_i32), ("n_bnd", _c_i32),
+                ("wuni", ctypes.POINTER(_c_f64)), ("w_bnd", ctypes.POINTER(_c_f64)),
+                ("start_bnd", ctypes.POINTER(_c_i32))]
+
+
+def uniform_rows(band, n_out):
+    """Build the pt_uniform_rows argument from a band dict (keys w, lo, hi, wuni, wmax, start,
+    weights); returns None for non-uniform bands.  The arrays are kept alive on the struct."""
+    if band.get("wuni") is None:
+        return None
+    lo, hi, wmax = int(band["lo"]), int(band["hi"]), int(band["wmax"])
+    rows = list(range(0, lo)) + list(range(hi, n_out))
+    u = UniformRows()
+    u.w_uni, u.lo, u.hi, u.n_bnd = int(band["w"]), lo, hi, len(rows)
+    u._wuni = (ctypes.c_double * int(band["w"]))(*np.asarray(band["wuni"], dtype=np.float64).tolist())
+    u.wuni = ctypes.cast(u._wuni, ctypes.POINTER(_c_f64))
+    if rows and len(rows) <= 8:
+        wb = np.ascontiguousarray(np.asarray(band["weights"])[rows], dtype=np.float64).ravel()
+        sb = np.ascontiguousarray(np.asarray(band["start"])[rows], dtype=np.int32)
+        u._wb = (ctypes.c_double * wb.size)(*wb.tolist())
+        u._sb = (ctypes.c_int32 * sb.size)(*sb.tolist())
+        u.w_bnd = ctypes.cast(u._wb, ctypes.POINTER(_c_f64))
+        u.start_bnd = ctypes.cast(u._sb, ctypes.POINTER(_c_i32))
+    return u
+
+
 # name -> (restype, argtypes); mirrors include/pytristan_b200.h one to one
 SIGNATURES = {
     "pt_last_error": (ctypes.c_char_p, []),
@@ -38,11 +69,9 @@ SIGNATURES = {
     "pt_dense_apply": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64,
                                 _c_f64, _c_ptr, _c_i32, _c_i64, _c_ptr]),
     "pt_stencil_apply": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64,
-                                  _c_i32, ctypes.POINTER(_c_f64), _c_i32, _c_i32, _c_i32, _c_f64,
-                                  _c_f64, _c_ptr]),
+                                  _c_i32, ctypes.POINTER(UniformRows), _c_f64, _c_f64, _c_ptr]),
     "pt_stencil_apply_ex": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64,
-                                     _c_i64, _c_i32, ctypes.POINTER(_c_f64), _c_i32, _c_i32, _c_i32,
-                                     _c_f64, _c_f64, _c_ptr]),
+                                     _c_i64, _c_i32, ctypes.POINTER(UniformRows), _c_f64, _c_f64, _c_ptr]),
     "pt_permute3d": (_c_i32, [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_i64, _c_i32, _c_ptr]),
     "pt_measure_dmma_peak": (_c_i32, [ctypes.POINTER(_c_f64), _c_i32]),
 }

@@ -21,7 +21,15 @@ namespace {
 
 constexpr int MAXW = 16;
 
-struct UniWeights { double w[MAXW]; };
+constexpr int MAXBND = 8;    // boundary rows that can ride in the kernel parameters
+constexpr int MAXBW = 10;    // widest boundary stencil kept there
+
+struct UniWeights {
+  double w[MAXW];
+  double wb[MAXBND][MAXBW];  // boundary rows: top rows first, then bottom rows
+  int sb[MAXBND];
+  int n_bnd;                 // 0: boundary rows are not in the parameters
+};
 
 struct StencilParams {
   const double* __restrict__ W;
@@ -160,7 +168,35 @@ __global__ void __launch_bounds__(128) stencil_strided_kernel(const StencilParam
 
 // ---- K3: contiguous axis, shared-memory tile ---------------------------------------------------------
 // Block = 256 threads, tile = ROWS rows x TI points (TI even), halo HL = 4 doubles each side.
-// V = 2: 16-byte staging loads (n even, 16-byte aligned base); V = 1: 8-byte staging.
+// V = 2: 16-byte cp.async staging (n_in, n_out, shift even, 16-byte aligned bases); V = 1: 8-byte.
+// The tile is staged with cp.async (no register staging, all copies of a thread in flight at
+// once); chunks that straddle the ends of the axis are filled by plain stores (zero or wrapped).
+__device__ __forceinline__ void st_cp_async16(void* smem, const void* gmem) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void st_cp_async8(void* smem, const void* gmem) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+
+// one boundary row evaluated from the staged tile with the weights held in the kernel parameters
+// (falls back to global memory for inputs that a tile boundary left outside the staged window)
+__device__ __forceinline__ double boundary_from_tile(const StencilParams& p, const UniWeights& uw,
+                                                     const double* srow, const double* rowp, int i,
+                                                     int jbase, int pitch) {
+  const int bi = i < p.lo ? i : p.lo + (i - p.hi);
+  const int s0 = uw.sb[bi];
+  double acc = 0.0;
+  for (int s = 0; s < p.wmax; ++s) {
+    const int j = s0 + s;
+    const int l = j - jbase;
+    const double u = (l >= 0 && l < pitch) ? srow[l] : rowp[j];
+    acc = fma(uw.wb[bi][s], u, acc);
+  }
+  return acc;
+}
+
 template <int W, int V>
 __global__ void __launch_bounds__(256) stencil_contig_kernel(const StencilParams p,
                                                               const UniWeights uw, int TI, int ROWS,
@@ -170,41 +206,44 @@ __global__ void __launch_bounds__(256) stencil_contig_kernel(const StencilParams
   extern __shared__ __align__(16) double sm[];
   const int pitch = TI + 2 * HL;
   const int n = p.n;
-  const int64_t tile = blockIdx.x;
-  const int ti = int(tile % tiles_per_row);
-  const int64_t row0 = (tile / tiles_per_row) * ROWS;
+  const int ti = int(blockIdx.x % tiles_per_row);
+  const int64_t row0 = int64_t(blockIdx.x / tiles_per_row) * ROWS;
   const int i0 = ti * TI;
   const int tid = threadIdx.x;
+  const int64_t rows_left = p.after - row0;
+  const int nrows = rows_left < ROWS ? int(rows_left) : ROWS;
+  const int jbase = i0 + p.shift - HL;   // input index of the first staged double of a row
 
-  // ---- stage: ROWS x (TI + 8) doubles; chunk = V doubles
+  // ---- stage
   const int cpr = pitch / V;
-  for (int idx = tid; idx < ROWS * cpr; idx += 256) {
-    const int r = idx / cpr;
-    const int c = (idx - r * cpr) * V;      // offset inside the padded row
-    const int64_t a = row0 + r;
-    if (a >= p.after) continue;
-    int j = i0 + p.shift - HL + c;           // input index of the first double of the chunk
-    const double* rowp = p.U + a * int64_t(n);
-    double* dst = sm + r * pitch + c;
-    if (V == 2) {
-      double2 val = make_double2(0.0, 0.0);
-      if (j >= 0 && j + 1 < n) {
-        val = *reinterpret_cast<const double2*>(rowp + j);
-      } else if (p.periodic) {
-        val.x = rowp[wrap_index(j, n)];
-        val.y = rowp[wrap_index(j + 1, n)];
+  for (int r = 0; r < nrows; ++r) {
+    const double* rowp = p.U + (row0 + r) * int64_t(n);
+    double* srow = sm + r * pitch;
+    for (int c = tid; c < cpr; c += 256) {
+      const int j = jbase + c * V;
+      double* dst = srow + c * V;
+      if (V == 2) {
+        if (j >= 0 && j + 1 < n) {
+          st_cp_async16(dst, rowp + j);
+        } else {
+          double2 val = make_double2(0.0, 0.0);
+          if (p.periodic) {
+            val.x = rowp[wrap_index(j, n)];
+            val.y = rowp[wrap_index(j + 1, n)];
+          } else {
+            if (j >= 0 && j < n) val.x = rowp[j];
+            if (j + 1 >= 0 && j + 1 < n) val.y = rowp[j + 1];
+          }
+          *reinterpret_cast<double2*>(dst) = val;
+        }
       } else {
-        if (j >= 0 && j < n) val.x = rowp[j];
-        if (j + 1 >= 0 && j + 1 < n) val.y = rowp[j + 1];
+        if (j >= 0 && j < n) st_cp_async8(dst, rowp + j);
+        else *dst = p.periodic ? rowp[wrap_index(j, n)] : 0.0;
       }
-      *reinterpret_cast<double2*>(dst) = val;
-    } else {
-      double val = 0.0;
-      if (j >= 0 && j < n) val = rowp[j];
-      else if (p.periodic) val = rowp[wrap_index(j, n)];
-      *dst = val;
     }
   }
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
   __syncthreads();
 
   double w[W];
@@ -213,39 +252,59 @@ __global__ void __launch_bounds__(256) stencil_contig_kernel(const StencilParams
   const bool use_beta = p.beta != 0.0;
 
   // ---- compute: each item = 2 adjacent points
+  auto rowp_of = [&](int r) { return p.U + (row0 + r) * int64_t(n); };
   const int ipr = TI / 2;  // items per row
-  for (int idx = tid; idx < ROWS * ipr; idx += 256) {
-    const int r = idx / ipr;
-    const int li = (idx - r * ipr) * 2;   // local point index (even)
-    const int64_t a = row0 + r;
-    const int i = i0 + li;
-    if (a >= p.after || i >= p.n_out) continue;
-    const double* s = sm + r * pitch + li;  // s[0] is input point i + shift - HL
-    double v[10];
+  for (int r = 0; r < nrows; ++r) {
+    const double* srow = sm + r * pitch;
+    double* yrow = p.Y + (row0 + r) * int64_t(p.n_out);
+    for (int it = tid; it < ipr; it += 256) {
+      const int li = it * 2;
+      const int i = i0 + li;
+      if (i >= p.n_out) break;
+      const double* s = srow + li;  // s[0] is input point i + shift - HL
+      double v[10];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const double2 t2 = *reinterpret_cast<const double2*>(s + 2 * k);
-      v[2 * k] = t2.x; v[2 * k + 1] = t2.y;
-    }
-    double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-    for (int q = 0; q < W; ++q) {
-      acc0 = fma(w[q], v[HL - HW + q], acc0);
-      acc1 = fma(w[q], v[HL - HW + 1 + q], acc1);
-    }
-    double* yp = p.Y + a * int64_t(p.n_out) + i;
-    const bool ok0 = (i >= p.lo && i < p.hi);
-    const bool ok1 = (i + 1 >= p.lo && i + 1 < p.hi);  // i + 1 < n implied by hi <= n
-    if (V == 2 && ok0 && ok1) {
-      double2 o = make_double2(p.alpha * acc0, p.alpha * acc1);
-      if (use_beta) {
-        const double2 old = *reinterpret_cast<const double2*>(yp);
-        o.x = fma(p.beta, old.x, o.x); o.y = fma(p.beta, old.y, o.y);
+      for (int k = 0; k < 5; ++k) {
+        const double2 t2 = *reinterpret_cast<const double2*>(s + 2 * k);
+        v[2 * k] = t2.x; v[2 * k + 1] = t2.y;
       }
-      *reinterpret_cast<double2*>(yp) = o;
-    } else {
-      if (ok0) { double o = p.alpha * acc0; if (use_beta) o = fma(p.beta, yp[0], o); yp[0] = o; }
-      if (ok1) { double o = p.alpha * acc1; if (use_beta) o = fma(p.beta, yp[1], o); yp[1] = o; }
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < W; ++q) {
+        acc0 = fma(w[q], v[HL - HW + q], acc0);
+        acc1 = fma(w[q], v[HL - HW + 1 + q], acc1);
+      }
+      double* yp = yrow + i;
+      const bool ok0 = (i >= p.lo && i < p.hi);
+      const bool ok1 = (i + 1 >= p.lo && i + 1 < p.hi);
+      if (V == 2 && ok0 && ok1) {
+        double2 o = make_double2(p.alpha * acc0, p.alpha * acc1);
+        if (use_beta) {
+          const double2 old = *reinterpret_cast<const double2*>(yp);
+          o.x = fma(p.beta, old.x, o.x); o.y = fma(p.beta, old.y, o.y);
+        }
+        *reinterpret_cast<double2*>(yp) = o;
+      } else {
+        if (ok0) { double o = p.alpha * acc0; if (use_beta) o = fma(p.beta, yp[0], o); yp[0] = o; }
+        if (ok1) { double o = p.alpha * acc1; if (use_beta) o = fma(p.beta, yp[1], o); yp[1] = o; }
+      }
+    }
+  }
+
+  // ---- boundary rows (one-sided closures): one thread per (row, boundary point), weights from
+  // the kernel parameters, inputs from the same tile.  Kept out of the main loop so that no
+  // warp of the streaming part diverges.
+  if (uw.n_bnd > 0) {
+    for (int t = tid; t < nrows * uw.n_bnd; t += 256) {
+      const int r = t / uw.n_bnd;
+      const int bi = t - r * uw.n_bnd;
+      const int i = bi < p.lo ? bi : p.hi + (bi - p.lo);
+      if (i < i0 || i >= i0 + TI) continue;   // another tile of the row owns this point
+      const double v = boundary_from_tile(p, uw, sm + r * pitch, rowp_of(r), i, jbase, pitch);
+      double* yp = p.Y + (row0 + r) * int64_t(p.n_out) + i;
+      double o = p.alpha * v;
+      if (use_beta) o = fma(p.beta, *yp, o);
+      *yp = o;
     }
   }
 }
@@ -317,7 +376,7 @@ int launch_contig(const StencilParams& p, const UniWeights& uw, cudaStream_t st)
 template <int W>
 int launch_fast(const StencilParams& p, const UniWeights& uw, cudaStream_t st) {
   int rc = (p.before == 1) ? launch_contig<W>(p, uw, st) : launch_strided<W>(p, uw, st);
-  if (rc) return rc;
+  if (rc || (p.before == 1 && uw.n_bnd > 0)) return rc;  // boundary rows were computed in the tile
   return launch_table(p, p.lo, p.hi, st);  // boundary rows
 }
 
@@ -325,8 +384,8 @@ int launch_fast(const StencilParams& p, const UniWeights& uw, cudaStream_t st) {
 
 extern "C" int pt_stencil_apply_ex(const double* W, const int32_t* start, int wmax, int n_in, int n_out,
                                    int shift, const double* U, double* Y, int64_t after, int64_t before,
-                                   int periodic, const double* wuni_host, int w_uni, int lo, int hi,
-                                   double alpha, double beta, pt_stream_t stream) {
+                                   int periodic, const pt_uniform_rows* uni, double alpha, double beta,
+                                   pt_stream_t stream) {
   PT_REQUIRE(W && start && U && Y, "pt_stencil_apply: null pointer");
   PT_REQUIRE(wmax >= 1 && wmax <= MAXW, "pt_stencil_apply: wmax=%d outside [1,%d]", wmax, MAXW);
   PT_REQUIRE(n_in >= 1 && n_in >= wmax, "pt_stencil_apply: n=%d smaller than the stencil width %d", n_in, wmax);
@@ -344,14 +403,26 @@ extern "C" int pt_stencil_apply_ex(const double* W, const int32_t* start, int wm
   cudaStream_t st = pt::as_stream(stream);
 
   // canonical rows must read inside the input slab: i + shift - hw >= 0 and i + shift + hw < n_in
+  const int w_uni = uni ? uni->w_uni : 0;
+  const int lo = uni ? uni->lo : 0, hi = uni ? uni->hi : 0;
   const int hwu = w_uni / 2;
-  const bool fast = wuni_host != nullptr && (w_uni == 3 || w_uni == 5 || w_uni == 7 || w_uni == 9) &&
+  const bool fast = uni != nullptr && uni->wuni != nullptr &&
+                    (w_uni == 3 || w_uni == 5 || w_uni == 7 || w_uni == 9) &&
                     lo >= 0 && hi <= n_out && hi - lo >= 2 * w_uni &&
                     (periodic || (lo + shift >= hwu && hi + shift <= n_in - hwu));
   if (!fast) return launch_table(p, 0, 0, st);  // every row through the table
 
   UniWeights uw;
-  for (int s = 0; s < MAXW; ++s) uw.w[s] = s < w_uni ? wuni_host[s] : 0.0;
+  for (int s = 0; s < MAXW; ++s) uw.w[s] = s < w_uni ? uni->wuni[s] : 0.0;
+  uw.n_bnd = 0;
+  const int n_bnd = lo + (n_out - hi);
+  if (n_bnd > 0 && n_bnd <= MAXBND && wmax <= MAXBW && uni->n_bnd == n_bnd && uni->w_bnd && uni->start_bnd) {
+    uw.n_bnd = n_bnd;
+    for (int r = 0; r < n_bnd; ++r) {
+      uw.sb[r] = uni->start_bnd[r];
+      for (int s = 0; s < MAXBW; ++s) uw.wb[r][s] = s < wmax ? uni->w_bnd[r * wmax + s] : 0.0;
+    }
+  }
   p.lo = lo; p.hi = hi;
   switch (w_uni) {
     case 3: return launch_fast<3>(p, uw, st);
@@ -363,8 +434,8 @@ extern "C" int pt_stencil_apply_ex(const double* W, const int32_t* start, int wm
 
 extern "C" int pt_stencil_apply(const double* W, const int32_t* start, int wmax, int n,
                                 const double* U, double* Y, int64_t after, int64_t before,
-                                int periodic, const double* wuni_host, int w_uni, int lo, int hi,
-                                double alpha, double beta, pt_stream_t stream) {
-  return pt_stencil_apply_ex(W, start, wmax, n, n, 0, U, Y, after, before, periodic, wuni_host, w_uni, lo,
-                             hi, alpha, beta, stream);
+                                int periodic, const pt_uniform_rows* uni, double alpha, double beta,
+                                pt_stream_t stream) {
+  return pt_stencil_apply_ex(W, start, wmax, n, n, 0, U, Y, after, before, periodic, uni, alpha, beta,
+                             stream);
 }

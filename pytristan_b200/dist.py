@@ -45,15 +45,14 @@ def _permute3d(src, dst, d2, d1, d0, perm):
 
 def _stencil_local(band, ext, out, n_in, n_out, shift, after, before, alpha, beta):
     lib = _lib.load()
-    if band["wuni"] is not None:
-        wuni = (ctypes.c_double * band["w"])(*band["wuni"].tolist())
-        w_uni = band["w"]
-    else:
-        wuni, w_uni = None, 0
+    if "uni" not in band:
+        band["uni"] = _lib.uniform_rows(band, n_out)
+    uni = band["uni"]
     _lib.check(
         lib.pt_stencil_apply_ex(_lib.dptr(band["d_w"]), _lib.dptr(band["d_start"]), band["wmax"], n_in,
-                                n_out, shift, _lib.dptr(ext), _lib.dptr(out), after, before, 0, wuni, w_uni,
-                                band["lo"], band["hi"], float(alpha), float(beta), _lib.stream_ptr()),
+                                n_out, shift, _lib.dptr(ext), _lib.dptr(out), after, before, 0,
+                                ctypes.byref(uni) if uni is not None else None, float(alpha), float(beta),
+                                _lib.stream_ptr()),
         "pt_stencil_apply_ex",
     )
 

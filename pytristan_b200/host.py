@@ -112,8 +112,8 @@ def launches_per_apply(ops, after=1):
         band = getattr(op, "_band", None)
         if band is None:
             count += 1
-        elif band["wuni"] is not None and not band["periodic"]:
-            count += 2          # interior kernel + boundary-row table kernel
+        elif band["wuni"] is not None and not band["periodic"] and op.axis != 0:
+            count += 2          # strided interior kernel + boundary-row table kernel
         else:
             count += 1
     return count

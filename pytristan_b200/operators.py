@@ -428,15 +428,13 @@ class FinDiffMat(_DiffMat):
         lib = _lib.load()
         band = self._band
         d_y = self._prepare_out(d_u, out, beta)
-        if band["wuni"] is not None:
-            wuni = (ctypes.c_double * band["w"])(*band["wuni"].tolist())
-            w_uni = band["w"]
-        else:
-            wuni, w_uni = None, 0
+        if "uni" not in band:
+            band["uni"] = _lib.uniform_rows(band, n)
+        uni = band["uni"]
         _lib.check(
             lib.pt_stencil_apply(_lib.dptr(band["d_w"]), _lib.dptr(band["d_start"]), band["wmax"],
                                  n, _lib.dptr(d_u), _lib.dptr(d_y), after, before,
-                                 int(band["periodic"]), wuni, w_uni, band["lo"], band["hi"],
+                                 int(band["periodic"]), ctypes.byref(uni) if uni is not None else None,
                                  float(alpha), float(beta), _lib.stream_ptr()),
             "pt_stencil_apply",
         )

@@ -49,7 +49,7 @@ def test_argument_validation_needs_no_gpu():
     rc = lib.pt_gen_fornberg(None, 10, 1, 3, 0, 1, 0.1, ctypes.c_void_p(16), ctypes.c_void_p(16), 4, None)
     assert rc == -1 and b"even" in lib.pt_last_error()
     rc = lib.pt_stencil_apply(ctypes.c_void_p(16), ctypes.c_void_p(16), 7, 5, ctypes.c_void_p(16), ctypes.c_void_p(32),
-                              1, 1, 0, None, 0, 0, 0, 1.0, 0.0, None)
+                              1, 1, 0, None, 1.0, 0.0, None)
     assert rc == -1 and b"smaller than the stencil" in lib.pt_last_error()
     rc = lib.pt_grid_expand(None, (ctypes.c_int64 * 1)(4), 1, 3, None, None)
     assert rc in (-1, -3)
