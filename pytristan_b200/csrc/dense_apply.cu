@@ -239,14 +239,15 @@ dense_apply_kernel(const DenseParams p) {
   // fast loader for chunks that lie entirely inside the k range: running pointers, no index
   // arithmetic in the loop (chunks are always loaded in increasing order).  The loader burst is
   // what keeps a warp away from the tensor pipe, so it is kept to a few instructions per copy.
-  constexpr int ASUB = (C::BM * 2) / C::NT;  // 16-byte pieces of one operator panel per thread
-  static_assert((C::BM * 2) % C::NT == 0, "operator loader shape");
+  constexpr int ASUB = (C::BM * 2 + C::NT - 1) / C::NT;  // 16-byte pieces of one operator panel per thread
   const int64_t a_panel = int64_t(p.MP) * 4;
   const double* a_ptr = p.Dp + size_t(m0) * 4 + tid * 2;
-  unsigned a_ok = 0;
+  unsigned a_ok = 0, a_in = 0;  // row is valid / piece lies inside the panel
 #pragma unroll
-  for (int sub = 0; sub < ASUB; ++sub)
+  for (int sub = 0; sub < ASUB; ++sub) {
     if (((tid + sub * C::NT) >> 1) < rows_blk) a_ok |= 1u << sub;
+    if (tid + sub * C::NT < C::BM * 2) a_in |= 1u << sub;
+  }
   const double* b_ptr;
   int64_t b_rstep;
   unsigned b_ok = 0;
@@ -272,8 +273,9 @@ dense_apply_kernel(const DenseParams p) {
 #pragma unroll
       for (int sub = 0; sub < ASUB; ++sub) {
         const bool ok = (a_ok >> sub) & 1u;
-        cp_async16(As + pp * C::BM * 4 + (tid + sub * C::NT) * 2,
-                   ok ? a_ptr + pp * a_panel + sub * C::NT * 2 : p.Dp, ok ? 16 : 0);
+        if ((C::BM * 2) % C::NT == 0 || ((a_in >> sub) & 1u))
+          cp_async16(As + pp * C::BM * 4 + (tid + sub * C::NT) * 2,
+                     ok ? a_ptr + pp * a_panel + sub * C::NT * 2 : p.Dp, ok ? 16 : 0);
       }
     a_ptr += BKP * a_panel;
     constexpr int BR = KCONTIG ? C::BN / RPP2 : C::BK / RPP1;
@@ -415,14 +417,23 @@ int launch_cfg(DenseParams& p, cudaStream_t stream) {
   return pt::check_launch("pt_dense_apply");
 }
 
-int g_dense_config = 5;  // tuning hook (pt_debug_set_dense_config); 5 = default
+int g_dense_config = -1;  // tuning hook (pt_debug_set_dense_config); -1 = choose by shape
 
 template <bool KCONTIG, bool VEC16>
 int launch_shape(DenseParams& p, cudaStream_t stream) {
-  switch (g_dense_config) {
+  int cfg = g_dense_config;
+  if (cfg < 0) {
+    // measured on B200 (tools/sweep_dense.py, profiles/r01_dense_config_sweep.md): the 96x64 tile
+    // with 3 CTAs/SM wins everywhere except when n_out is a large multiple of 128, where the
+    // 128x64 tile with 2 CTAs/SM has no ragged last block and slightly better operand reuse
+    cfg = (p.n_out >= 1024 && p.n_out % 128 == 0) ? 5 : 9;
+  }
+  switch (cfg) {
     case 2: return launch_cfg<2, 4, 8, 4, 8, 3, KCONTIG, VEC16>(p, stream);   // BK = 32, 3 stages
     case 6: return launch_cfg<2, 2, 8, 4, 8, 2, KCONTIG, VEC16, 2>(p, stream);  // same, BK = 32, 2 stages
     case 0: return launch_cfg<2, 4, 8, 4, 4, 4, KCONTIG, VEC16>(p, stream);  // 8 warps, 64x32 per warp
+    case 8: return launch_cfg<1, 4, 16, 2, 4, 4, KCONTIG, VEC16, 2>(p, stream); // 4 warps along N, 128x16 per warp
+    case 9: return launch_cfg<1, 4, 12, 2, 4, 3, KCONTIG, VEC16, 3>(p, stream); // 96x16 per warp, 3 CTAs/SM
     default: return launch_cfg<2, 2, 8, 4, 4, 4, KCONTIG, VEC16, 2>(p, stream);
   }
 }

@@ -456,22 +456,28 @@ class PolarLaplacian:
     1/r^2 scaling fused in its epilogue (``pt_dense_apply`` with PT_SCALE_AFTER).
     """
 
-    def __init__(self, grid):
+    def __init__(self, grid, radial="cheb", accuracy=6):
         if isinstance(grid, (int, np.integer)):
             grid = getattr(_get_grid_manager(), str(int(grid)))
         if grid.num_dim != 2:
             raise ValueError("PolarLaplacian needs a 2-D polar grid")
+        if radial not in ("cheb", "findiff"):
+            raise ValueError("radial must be 'cheb' (CGL radial nodes) or 'findiff' (any mapped mesh)")
         self.npts = tuple(grid.npts)
         r = grid.axpoints(1)
         if np.any(r == 0.0):
             raise ValueError("the radial axis has a node at r = 0 (use fornberg=True)")
         self.r = r
-        d1 = ChebMat(grid, axis=1, order=1)
-        d2 = ChebMat(grid, axis=1, order=2)
-        torch = _lib.require_cuda()
+        if radial == "cheb":
+            d1 = ChebMat(grid, axis=1, order=1)
+            d2 = ChebMat(grid, axis=1, order=2)
+        else:   # arbitrary (mapped, non-uniform) radial mesh: Fornberg weights on the actual nodes
+            d1 = FinDiffMat(grid, axis=1, order=1, accuracy=accuracy)
+            d2 = FinDiffMat(grid, axis=1, order=2, accuracy=accuracy)
+        _lib.require_cuda()
         d_r = _lib.to_device(r)
-        radial = d2.device() + d1.device() / d_r[:, None]
-        self.radial = _DiffMat._wrap(radial, self.npts, 1, 2, grid.num)
+        radial_mat = d2.device() + d1.device() / d_r[:, None]
+        self.radial = _DiffMat._wrap(radial_mat, self.npts, 1, 2, grid.num)
         self.azimuthal = FourMat(grid, axis=0, order=2)
         self.inv_r2 = 1.0 / (d_r * d_r)
 
