@@ -77,7 +77,9 @@ def test_config3_polar_laplacian_full(radial):
     T, R = np.asarray(g)[0], np.asarray(g)[1]
     th, r = g.axpoints(0), g.axpoints(1)
     # analytic: r^2 -> 4 ; r^3 cos(3 theta) is harmonic
-    tol = 1e-6 if radial == "cheb" else 2e-3
+    # Chebyshev D2 at N = 512 carries O(N^4 eps) ~ 1e-5 rounding at the end nodes (inherent to the
+    # collocation matrix, the oracle shows the same); the FD variant is truncation limited
+    tol = 1e-4 if radial == "cheb" else 2e-3
     assert np.max(np.abs(lap.apply(R ** 2) - 4.0)) < tol
     assert np.max(np.abs(lap.apply(R ** 3 * np.cos(3 * T)))) < tol * 10
     # oracle on 2 sampled fields of a batch of 16 random fields
