@@ -63,6 +63,18 @@ def workload_spec(name):
         return dict(name=name, npts=(8192, 2048), batch=1, bound="tensor",
                     ops=[("ChebMat n=2048 on 8192 fields (K1)", "cheb", 1, 1, 2.0 * 2048 * 2048 * 8192)],
                     points_per_step=2048 * 8192)
+    if name == "fd6_1024cube_slab" or name == "fd6_512cube_slab":
+        n = 1024 if "1024" in name else 512
+        P = n ** 3
+        return dict(name=name, kind="slab", n=n, npts=(n, n, n), batch=1, bound="hbm", scaling="strong",
+                    ops=[("d/dx + d/dy + d/dz FinDiffMat 7-pt, z slab-sharded, halo exchange", "findiff", 2, 1, 3 * 16.0 * P)],
+                    points_per_step=3 * P)
+    if name == "cheb512cube_pencil" or name == "cheb256cube_pencil":
+        n = 512 if "512" in name else 256
+        P = n ** 3
+        return dict(name=name, kind="pencil", n=n, npts=(n, n, n), batch=1, bound="tensor", scaling="strong",
+                    ops=[("D2x + D2y + D2z ChebMat on pencils (2 all-to-all rounds)", "cheb", 0, 2, 3 * 2.0 * n * P)],
+                    points_per_step=3 * P)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -377,11 +389,118 @@ def run_gpu(args, spec):
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": nbytes,
                 "d2h_bytes_per_step": nbytes * len(ops), "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "api": "pytristan_b200.apply_host(ops, pinned_host_fields, pinned_host_outputs)"},
-        "gpu_launches": args.steps * pt.launches_per_apply(ops),
+        "gpu_launches": args.steps * pt.launches_per_apply(ops) * world,
         "clocks": sampler.summary(),
     }
     print(json.dumps(line))
     if world > 1:
+        dist.destroy_process_group()
+
+
+def run_gpu_sharded(args, spec):
+    """Strong-scaling workloads where the differentiated axes are sharded (SURVEY.md 8e ii/iii):
+    slab-sharded 3-axis stencil with halo exchange, and the three-axis Chebyshev operator on pencils."""
+    import torch
+    import torch.distributed as dist
+
+    import pytristan_b200 as pt
+    from pytristan_b200 import dist as ptd
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1 or spec["kind"] == "pencil":
+        if "MASTER_ADDR" not in os.environ:
+            os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", RANK="0", WORLD_SIZE="1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = spec["n"]
+    gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
+    if spec["kind"] == "slab":
+        x = np.linspace(0.0, 1.0, n)
+        F = pt.FinDiffMat(x, order=1, accuracy=6)
+        plan = ptd.SlabStencil.from_operator(F, rank, world)
+        fx, fy = pt.FinDiffMat(x, order=1, accuracy=6), pt.FinDiffMat(x, order=1, accuracy=6)
+        fx.npts, fx.axis = (n, n, plan.nloc), 0
+        fy.npts, fy.axis = (n, n, plan.nloc), 1
+        ext = torch.zeros(plan.ext_shape(1, n * n), dtype=torch.float64, device="cuda")
+        plan.interior(ext).copy_(torch.randn(1, plan.nloc, n * n, dtype=torch.float64, device="cuda", generator=gen))
+        own = plan.interior(ext)                       # contiguous: slabs of the slowest axis
+        outs = [torch.empty(plan.nloc * n * n, dtype=torch.float64, device="cuda") for _ in range(3)]
+
+        def step():
+            plan.exchange(ext)                          # halo planes over NVLink (NCCL send/recv)
+            fx.apply(own.reshape(-1), out=outs[0])
+            fy.apply(own.reshape(-1), out=outs[1])
+            plan.apply(ext, out=outs[2].view(1, plan.nloc, n * n))
+
+        launches = 5
+        local_alg = 3 * 16.0 * plan.nloc * n * n
+        host_bytes = plan.nloc * n * n * 8
+    else:
+        py = 2 if world % 2 == 0 else 1
+        pz = world // py
+        pen = ptd.PencilTranspose((n, n, n), py, pz, rank, world)
+        xs = pt.cheb(n)
+        ops = [pt.ChebMat(xs, order=2) for _ in range(3)]
+        u = torch.randn(pen.nzl, pen.nyl, n, dtype=torch.float64, device="cuda", generator=gen)
+
+        def step():
+            return ptd.pencil_apply_sum(ops, u, pen, back=False)
+
+        launches = 3 + 2 + 2 + 1          # 3 DMMA kernels, pack/unpack of two redistributions (z unpack only for batch)
+        local_alg = 3 * 2.0 * n * (n ** 3) / world
+        host_bytes = u.numel() * 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    with sampler:
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            step()
+        t1.record()
+        barrier()
+    ms = t0.elapsed_time(t1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = spec["points_per_step"] / (ms * 1e-3)
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        if spec["bound"] == "hbm":
+            peak = peaks.get("hbm_gbs", 6650.0)
+            ach = local_alg / (ms * 1e-3) * 1e-9
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "note": "per-GPU algorithmic bytes of the whole step (3 derivatives, 16 B/pt each) over the step time, halo exchange included"}
+        else:
+            ach = local_alg / (ms * 1e-3) * 1e-12
+            roof = {"bound": "tensor", "achieved": ach, "peak": 37.0, "unit": "TFLOP/s", "frac": ach / 37.0, "traffic": None,
+                    "note": "per-GPU algorithmic flops of the three applies over the whole step time (all-to-all rounds included); peak = measured FP64 DMMA 37.0 (profiles/r01_fp64_peak.json)"}
+        line = {"metric": "derivative grid-points/sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": spec["name"], "npts": list(spec["npts"]), "ops": [o[0] for o in spec["ops"]],
+                           "sharding": "z slabs + halo exchange" if spec["kind"] == "slab" else "2-D pencils, all_to_all redistributions",
+                           "l2": "per-rank field larger than L2" if host_bytes > 126e6 else "per-rank field fits L2 (strong scaling)"},
+                "roofline": roof, "cpu_baseline": None,
+                "e2e": None, "gpu_launches": args.steps * launches * world, "clocks": sampler.summary()}
+        print(json.dumps(line))
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 
@@ -397,6 +516,8 @@ def main():
     spec = workload_spec(args.workload)
     if args.impl == "reference":
         run_reference(args, spec)
+    elif spec.get("kind") in ("slab", "pencil"):
+        run_gpu_sharded(args, spec)
     else:
         run_gpu(args, spec)
 
