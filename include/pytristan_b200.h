@@ -140,6 +140,15 @@ int pt_stencil_apply_ex(const double* W, const int32_t* start, int wmax, int n_i
                         int periodic, const pt_uniform_rows* uni, double alpha, double beta,
                         pt_stream_t stream);
 
+/* Fused three-axis gradient of 3-D fields (nx fastest): GX, GY, GZ = d/dx, d/dy, d/dz of U in one
+ * read of U (32 B/pt instead of 3 x 16 B/pt).  W/start/wmax/uni are arrays of 3 (axis 0, 1, 2)
+ * with the same meaning as in pt_stencil_apply.  Returns PT_ERR_UNSUPPORTED (and does nothing)
+ * unless every axis is a non-periodic uniform axis with the same stencil width, nx is even and
+ * the fields are 16-byte aligned: callers then fall back to three pt_stencil_apply calls. */
+int pt_stencil_grad3(const double* U, double* GX, double* GY, double* GZ, int nx, int ny, int nz,
+                     int64_t nfields, const double* const* W, const int32_t* const* start,
+                     const int* wmax, const pt_uniform_rows* const* uni, pt_stream_t stream);
+
 /* ---- K7: pencil-transpose pack/unpack (multi-GPU) ----------------------------------------- */
 /* Generic 3-D permutation copy used on both sides of the all-to-all: in is (d2, d1, d0)
  * C-contiguous; out[perm] = in, perm one of the 6 axis orders encoded as p0 + 3*p1 + 9*p2

@@ -72,6 +72,9 @@ SIGNATURES = {
                                   _c_i32, ctypes.POINTER(UniformRows), _c_f64, _c_f64, _c_ptr]),
     "pt_stencil_apply_ex": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64,
                                      _c_i64, _c_i32, ctypes.POINTER(UniformRows), _c_f64, _c_f64, _c_ptr]),
+    "pt_stencil_grad3": (_c_i32, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i64,
+                                  ctypes.POINTER(_c_ptr), ctypes.POINTER(_c_ptr), ctypes.POINTER(_c_i32),
+                                  ctypes.POINTER(ctypes.POINTER(UniformRows)), _c_ptr]),
     "pt_permute3d": (_c_i32, [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_i64, _c_i32, _c_ptr]),
     "pt_measure_dmma_peak": (_c_i32, [ctypes.POINTER(_c_f64), _c_i32]),
 }

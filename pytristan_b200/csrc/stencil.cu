@@ -439,3 +439,202 @@ extern "C" int pt_stencil_apply(const double* W, const int32_t* start, int wmax,
   return pt_stencil_apply_ex(W, start, wmax, n, n, 0, U, Y, after, before, periodic, uni, alpha, beta,
                              stream);
 }
+
+// ---- fused three-axis gradient: d/dx, d/dy, d/dz of a 3-D field in ONE read of U ------------------
+// (8 B/pt read + 24 B/pt written = 32 B/pt instead of 3 x 16 B/pt.)
+// 2.5-D blocking: a CTA owns a 64 (x) x 16 (y) tile and marches along z.  Every thread keeps the
+// z-window of its two x-adjacent points in registers (dz), the current plane of the tile plus
+// halos lives in a double-buffered shared tile (dx from the row, dy from the column).  Halo cells
+// are prefetched one plane ahead.  Centred weights everywhere; the few one-sided boundary planes
+// of each axis are rewritten afterwards by the table kernel.
+namespace {
+
+struct Grad3Params {
+  const double* __restrict__ U;
+  double* __restrict__ G[3];
+  int nx, ny, nz;
+  int zchunk;
+  double w[3][MAXW];
+};
+
+template <int W, int TY>
+__global__ void __launch_bounds__(32 * TY, 1024 / (32 * TY)) stencil_grad3_kernel(const Grad3Params p) {
+  constexpr int HW = W / 2;
+  constexpr int HX = 4;              // x halo in doubles (even: keeps 16-byte alignment)
+  constexpr int TXP = 64;            // tile: 64 points in x (32 threads x double2), TY rows in y
+  constexpr int PITCH = TXP + 2 * HX;
+  constexpr int ROWS = TY + 2 * HW;
+  constexpr int PLANE = ROWS * PITCH;
+  __shared__ __align__(16) double sm[2][PLANE];
+
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * 32 + tx;
+  const int xb = blockIdx.x * TXP, yb = blockIdx.y * TY;
+  const int x0 = xb + 2 * tx, y = yb + ty;
+  const int z0 = blockIdx.z * p.zchunk;
+  const int z1 = min(z0 + p.zchunk, p.nz);
+  const int64_t plane = int64_t(p.nx) * p.ny;
+  const bool mine = (x0 < p.nx) && (y < p.ny);            // nx is even: x0 + 1 < nx as well
+  const double2 zero2 = make_double2(0.0, 0.0);
+  const double* up = p.U + int64_t(y) * p.nx + x0;         // + z*plane
+
+  // halo duty: 2*(TY) x-halo row pieces (2 double2 left, 2 right per row) + 2*HW full rows
+  constexpr int XH = TY * 4;                 // double2 chunks of the x halos
+  constexpr int YH = 2 * HW * (PITCH / 2);   // double2 chunks of the y halo rows
+  static_assert(XH + YH <= 32 * TY, "one halo chunk per thread");
+  int h_sm = -1;
+  int64_t h_off = 0;
+  bool h_ok = false;
+  if (tid < XH + YH) {
+    int row, col;  // position in the shared tile (row in [0,ROWS), col even in [0,PITCH))
+    if (tid < XH) {
+      row = HW + tid / 4;
+      const int q = tid % 4;
+      col = (q < 2) ? 2 * q : HX + TXP + 2 * (q - 2);
+    } else {
+      const int t = tid - XH;
+      const int r = t / (PITCH / 2);
+      row = r < HW ? r : TY + r;               // rows 0..HW-1 and TY+HW..TY+2HW-1
+      col = 2 * (t % (PITCH / 2));
+    }
+    const int gx = xb - HX + col, gy = yb - HW + row;
+    h_sm = row * PITCH + col;
+    h_ok = (gx >= 0) && (gx + 1 < p.nx) && (gy >= 0) && (gy < p.ny);
+    h_off = int64_t(gy) * p.nx + gx;
+  }
+
+  double wx[W], wy[W], wz[W];
+#pragma unroll
+  for (int s = 0; s < W; ++s) { wx[s] = p.w[0][s]; wy[s] = p.w[1][s]; wz[s] = p.w[2][s]; }
+
+  double2 win[W];
+#pragma unroll
+  for (int s = 0; s < W - 1; ++s) {
+    const int z = z0 - HW + s;
+    win[s] = (mine && z >= 0 && z < p.nz) ? *reinterpret_cast<const double2*>(up + z * plane) : zero2;
+  }
+  double2 hreg = (h_ok) ? *reinterpret_cast<const double2*>(p.U + z0 * plane + h_off) : zero2;
+
+  for (int z = z0; z < z1; ++z) {
+    const int zn = z + HW;
+    win[W - 1] = (mine && zn < p.nz) ? *reinterpret_cast<const double2*>(up + zn * plane) : zero2;
+    double* buf = sm[z & 1];
+    *reinterpret_cast<double2*>(buf + (ty + HW) * PITCH + HX + 2 * tx) = win[HW];
+    if (h_sm >= 0) {
+      *reinterpret_cast<double2*>(buf + h_sm) = hreg;
+      hreg = (h_ok && z + 1 < z1) ? *reinterpret_cast<const double2*>(p.U + (z + 1) * plane + h_off) : zero2;
+    }
+    __syncthreads();
+    if (mine) {
+      const double* rowp = buf + (ty + HW) * PITCH + 2 * tx;   // rowp[0] = point x0 - HX
+      double v[10];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const double2 t2 = *reinterpret_cast<const double2*>(rowp + 2 * k);
+        v[2 * k] = t2.x; v[2 * k + 1] = t2.y;
+      }
+      double2 gx2 = zero2, gy2 = zero2, gz2 = zero2;
+#pragma unroll
+      for (int s = 0; s < W; ++s) {
+        gx2.x = fma(wx[s], v[HX - HW + s], gx2.x);
+        gx2.y = fma(wx[s], v[HX - HW + 1 + s], gx2.y);
+        const double2 c = (s == HW) ? win[HW]
+                                    : *reinterpret_cast<const double2*>(buf + (ty + s) * PITCH + HX + 2 * tx);
+        gy2.x = fma(wy[s], c.x, gy2.x);
+        gy2.y = fma(wy[s], c.y, gy2.y);
+        gz2.x = fma(wz[s], win[s].x, gz2.x);
+        gz2.y = fma(wz[s], win[s].y, gz2.y);
+      }
+      const int64_t o = z * plane + int64_t(y) * p.nx + x0;
+      *reinterpret_cast<double2*>(p.G[0] + o) = gx2;
+      *reinterpret_cast<double2*>(p.G[1] + o) = gy2;
+      *reinterpret_cast<double2*>(p.G[2] + o) = gz2;
+    }
+#pragma unroll
+    for (int s = 0; s < W - 1; ++s) win[s] = win[s + 1];
+  }
+}
+
+int g_grad_ty = 16;  // tuning hook (pt_debug_set_grad_ty): 16 measured fastest at 1024^3
+
+template <int W>
+int launch_grad3(const Grad3Params& p, cudaStream_t st) {
+  const int ty = g_grad_ty;
+  const int gx = (p.nx + 63) / 64, gy = (p.ny + ty - 1) / ty;
+  const int gz = (p.nz + p.zchunk - 1) / p.zchunk;
+  if (gy > 65535 || gz > 65535) return pt::fail(PT_ERR_UNSUPPORTED, "pt_stencil_grad3: grid too large");
+  dim3 grid(gx, gy, gz), block(32, ty);
+  if (ty == 32) stencil_grad3_kernel<W, 32><<<grid, block, 0, st>>>(p);
+  else stencil_grad3_kernel<W, 16><<<grid, block, 0, st>>>(p);
+  return pt::check_launch("pt_stencil_grad3");
+}
+
+}  // namespace
+
+extern "C" int pt_debug_set_grad_ty(int ty) {
+  g_grad_ty = (ty == 16) ? 16 : 32;
+  return PT_OK;
+}
+
+extern "C" int pt_stencil_grad3(const double* U, double* GX, double* GY, double* GZ, int nx, int ny, int nz,
+                                int64_t nfields, const double* const* W, const int32_t* const* start,
+                                const int* wmax, const pt_uniform_rows* const* uni, pt_stream_t stream) {
+  PT_REQUIRE(U && GX && GY && GZ && W && start && wmax && uni, "pt_stencil_grad3: null pointer");
+  PT_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1 && nfields >= 0, "pt_stencil_grad3: bad shape");
+  PT_REQUIRE(U != GX && U != GY && U != GZ, "pt_stencil_grad3: in-place application is not supported");
+  const int dims[3] = {nx, ny, nz};
+  int w = 0;
+  for (int k = 0; k < 3; ++k) {
+    if (!uni[k] || !uni[k]->wuni) return pt::fail(PT_ERR_UNSUPPORTED, "pt_stencil_grad3: axis %d is not uniform", k);
+    if (k == 0) w = uni[k]->w_uni;
+    if (uni[k]->w_uni != w) return pt::fail(PT_ERR_UNSUPPORTED, "pt_stencil_grad3: stencil widths differ");
+    const int hw = w / 2;
+    if (uni[k]->lo != hw || uni[k]->hi != dims[k] - hw || dims[k] < 2 * w)
+      return pt::fail(PT_ERR_UNSUPPORTED, "pt_stencil_grad3: axis %d is not a plain non-periodic uniform axis", k);
+    PT_REQUIRE(W[k] && start[k] && wmax[k] >= 1 && wmax[k] <= MAXW, "pt_stencil_grad3: bad band for axis %d", k);
+  }
+  if (!(w == 3 || w == 5 || w == 7 || w == 9)) return pt::fail(PT_ERR_UNSUPPORTED, "pt_stencil_grad3: width %d", w);
+  if (nx % 2 || !aligned16(U) || !aligned16(GX) || !aligned16(GY) || !aligned16(GZ))
+    return pt::fail(PT_ERR_UNSUPPORTED, "pt_stencil_grad3: needs even nx and 16-byte aligned fields");
+  cudaStream_t st = pt::as_stream(stream);
+  const int64_t P = int64_t(nx) * ny * nz;
+  double* G[3] = {GX, GY, GZ};
+  for (int64_t f = 0; f < nfields; ++f) {
+    Grad3Params p;
+    p.U = U + f * P;
+    for (int k = 0; k < 3; ++k) {
+      p.G[k] = G[k] + f * P;
+      for (int s = 0; s < MAXW; ++s) p.w[k][s] = s < w ? uni[k]->wuni[s] : 0.0;
+    }
+    p.nx = nx; p.ny = ny; p.nz = nz;
+    // z-chunks: enough CTAs for a few waves, halo re-read (w-1 planes per chunk) kept small
+    const int64_t tiles = int64_t((nx + 63) / 64) * ((ny + g_grad_ty - 1) / g_grad_ty);
+    int chunks = int((int64_t(pt::sm_count()) * 8 + tiles - 1) / tiles);
+    if (chunks < 1) chunks = 1;
+    int zchunk = (nz + chunks - 1) / chunks;
+    if (zchunk < 8 * w) zchunk = 8 * w;
+    if (zchunk > nz) zchunk = nz;
+    p.zchunk = zchunk;
+    int rc;
+    switch (w) {
+      case 3: rc = launch_grad3<3>(p, st); break;
+      case 5: rc = launch_grad3<5>(p, st); break;
+      case 7: rc = launch_grad3<7>(p, st); break;
+      default: rc = launch_grad3<9>(p, st); break;
+    }
+    if (rc) return rc;
+    // one-sided boundary planes of each axis through the table
+    for (int k = 0; k < 3; ++k) {
+      StencilParams q;
+      q.W = W[k]; q.start = start[k]; q.U = p.U; q.Y = p.G[k];
+      q.wmax = wmax[k]; q.n = dims[k]; q.n_out = dims[k]; q.shift = 0;
+      q.before = (k == 0) ? 1 : (k == 1 ? nx : int64_t(nx) * ny);
+      q.after = P / (q.before * dims[k]);
+      q.periodic = 0; q.alpha = 1.0; q.beta = 0.0;
+      q.lo = uni[k]->lo; q.hi = uni[k]->hi;
+      rc = launch_table(q, q.lo, q.hi, st);
+      if (rc) return rc;
+    }
+  }
+  return PT_OK;
+}

@@ -362,3 +362,35 @@ def test_permute3d(dims):
         _lib.check(lib.pt_permute3d(_lib.dptr(t), _lib.dptr(out), d2, d1, d0, code, _lib.stream_ptr()), "permute")
         ref = np.ascontiguousarray(np.transpose(a, p))
         assert np.array_equal(out.cpu().numpy().reshape(ref.shape), ref), p
+
+
+# ---------------------------------------------------------------------------------------------
+# fused three-axis gradient
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("npts", [(64, 16, 14), (70, 33, 21), (130, 18, 40), (14, 14, 14)])
+@pytest.mark.parametrize("accuracy", [2, 6])
+def test_fused_gradient(npts, accuracy):
+    import pytristan_b200 as pt
+
+    torch = _torch()
+    axes = [np.linspace(0.0, 1.0 + k, n) for k, n in enumerate(npts)]
+    ops = []
+    for k in range(3):
+        F = pt.FinDiffMat(axes[k], order=1, accuracy=accuracy)
+        F.npts, F.axis = tuple(npts), k
+        ops.append(F)
+    rng = np.random.default_rng(1234)
+    U = rng.standard_normal((2, int(np.prod(npts))))
+    got = pt.gradient(ops, U)
+    for k in range(3):
+        band = oracle.findiff_band(axes[k], 1, accuracy)
+        ref = oracle.stencil_apply(band, U, npts, k)
+        assert np.max(np.abs(got[k] - ref)) <= 1e-12 * np.max(np.abs(ref)), k
+        assert np.array_equal(got[k], ops[k].apply(U)) or np.max(np.abs(got[k] - ops[k].apply(U))) <= 1e-13 * np.max(np.abs(ref))
+    # non-fusable combination (mapped axis) falls back to three passes, same answers
+    ops[1] = pt.FinDiffMat(oracle.cheb_nodes(npts[1], 0.0, 1.0), order=1, accuracy=accuracy)
+    ops[1].npts, ops[1].axis = tuple(npts), 1
+    got = pt.gradient(ops, torch.from_numpy(U).cuda())
+    band = oracle.findiff_band(oracle.cheb_nodes(npts[1], 0.0, 1.0), 1, accuracy)
+    ref = oracle.stencil_apply(band, U, npts, 1)
+    assert np.max(np.abs(got[1].cpu().numpy() - ref)) <= 1e-12 * np.max(np.abs(ref))

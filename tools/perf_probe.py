@@ -89,6 +89,18 @@ if __name__ == "__main__":
         stencil((1024, 1024, 512), 0, 1, "1024x1024x512 x (K3)")
         stencil((1024, 1024, 512), 1, 1, "1024x1024x512 y (K4)")
         stencil((1024, 1024, 512), 2, 1, "1024x1024x512 z (K4)")
+        import ctypes
+        _l = _lib.load(); _l.pt_debug_set_grad_ty.argtypes = [ctypes.c_int]
+        for n, ty in ((512, 16), (512, 32), (1024, 16), (1024, 32)):
+            _l.pt_debug_set_grad_ty(ty)
+            ops = []
+            for k in range(3):
+                F = pt.FinDiffMat(np.linspace(0, 1, n), order=1, accuracy=6); F.npts, F.axis = (n, n, n), k; ops.append(F)
+            U = torch.randn(n ** 3, dtype=torch.float64, device="cuda"); outs = [torch.empty_like(U) for _ in range(3)]
+            ms = timeit(lambda: pt.gradient(ops, U, outs=outs))
+            print(json.dumps({"case": f"fused gradient {n}^3 TY={ty}", "ms": round(ms, 4), "gbs_32B": round(32.0 * n ** 3 / ms * 1e-6, 1),
+                              "frac_hbm": round(32.0 * n ** 3 / ms * 1e-6 / HBM, 3), "gpts_s_x3": round(3 * n ** 3 / ms * 1e-6, 2)}))
+            del U, outs
         x = torch.randn(1 << 28, dtype=torch.float64, device="cuda"); y = torch.empty_like(x)
         ms = timeit(lambda: y.copy_(x))
         print(json.dumps({"case": "torch copy 2 GiB", "ms": round(ms, 4), "gbs": round(2 * x.numel() * 8 / ms * 1e-6, 1)}))
