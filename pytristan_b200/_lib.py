@@ -94,10 +94,17 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m pytristan_b200.build` "
-            "(pytristan_b200 has no CPU fallback)"
-        )
+        # the library is built in-tree by __graft_entry__.build(); as a safety net build it here
+        # when a toolkit is present (the GPU image has nvcc) — never fall back to a CPU path
+        try:
+            from .build import build as _build
+
+            _build()
+        except Exception as exc:
+            raise ImportError(
+                f"{LIB_PATH} is missing and could not be built ({exc}): run "
+                "`python -m pytristan_b200.build` (pytristan_b200 has no CPU fallback)"
+            ) from exc
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)

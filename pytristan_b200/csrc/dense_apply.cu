@@ -429,12 +429,8 @@ int launch_shape(DenseParams& p, cudaStream_t stream) {
     cfg = (p.n_out >= 1024 && p.n_out % 128 == 0) ? 5 : 9;
   }
   switch (cfg) {
-    case 2: return launch_cfg<2, 4, 8, 4, 8, 3, KCONTIG, VEC16>(p, stream);   // BK = 32, 3 stages
-    case 6: return launch_cfg<2, 2, 8, 4, 8, 2, KCONTIG, VEC16, 2>(p, stream);  // same, BK = 32, 2 stages
-    case 0: return launch_cfg<2, 4, 8, 4, 4, 4, KCONTIG, VEC16>(p, stream);  // 8 warps, 64x32 per warp
-    case 8: return launch_cfg<1, 4, 16, 2, 4, 4, KCONTIG, VEC16, 2>(p, stream); // 4 warps along N, 128x16 per warp
-    case 9: return launch_cfg<1, 4, 12, 2, 4, 3, KCONTIG, VEC16, 3>(p, stream); // 96x16 per warp, 3 CTAs/SM
-    default: return launch_cfg<2, 2, 8, 4, 4, 4, KCONTIG, VEC16, 2>(p, stream);
+    case 5: return launch_cfg<2, 2, 8, 4, 4, 4, KCONTIG, VEC16, 2>(p, stream);   // 64x32 per warp, 128x64 CTA, 2 CTAs/SM
+    default: return launch_cfg<1, 4, 12, 2, 4, 3, KCONTIG, VEC16, 3>(p, stream); // 96x16 per warp,  96x64 CTA, 3 CTAs/SM
   }
 }
 

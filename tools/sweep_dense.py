@@ -7,7 +7,7 @@ from pytristan_b200.operators import _DiffMat
 from tools.perf_probe import timeit
 lib = _lib.load(); lib.pt_debug_set_dense_config.argtypes = [ctypes.c_int]
 cfgs = [int(c) for c in sys.argv[1].split(",")]
-for n in (64, 96, 128, 129, 192, 256, 257, 384, 512, 513, 768, 1024, 1025, 1536, 2048, 2049):
+for n in (int(v) for v in (sys.argv[2].split(',') if len(sys.argv) > 2 else '64,96,128,129,192,256,257,384,512,513,768,1024,1025,1536,2048,2049'.split(','))):
     for axis in (0, 1):
         cols = max(4096, (1 << 25) // n // 64 * 64)
         npts = (n, cols) if axis == 0 else (cols, n)
