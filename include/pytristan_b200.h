@@ -75,9 +75,20 @@ int pt_grid_axpoints(const double* grid_row, int64_t stride, int64_t n, double* 
  * image of the CGL set, either orientation).  D is n*n row-major.  Recursion of Welfert with
  * the negative-sum diagonal, sequential summation order (oracle/operators.py:cheb_mat). */
 int pt_gen_chebmat(const double* x, int n, int order, double* D, pt_stream_t stream);
+/* Polynomial collocation differentiation matrix on ARBITRARY distinct nodes (a non-affine
+ * mapper of the reference, grid.py:201-207, returns nodes only): barycentric weights
+ * w_j = 1/prod(x_j - x_k) held as mantissa*2^exponent, D1_ij = (w_j/w_i)/(x_i-x_j), higher
+ * orders by the same recursion as pt_gen_chebmat.  work: 2*n doubles.
+ * (oracle/operators.py:bary_mat). */
+int pt_gen_barymat(const double* x, int n, int order, double* D, double* work, pt_stream_t stream);
 /* Fourier spectral differentiation matrix (order 1 or 2) for n equispaced periodic nodes on a
  * period `period`.  D is n*n row-major, circulant (oracle/operators.py:four_mat). */
 int pt_gen_fourmat(int n, double period, int order, double* D, pt_stream_t stream);
+/* Fourier differentiation matrix of any order 1..8 by direct summation of the symbol (i k s)^p
+ * over the retained modes (Nyquist mode dropped for odd orders).  work: n doubles.
+ * (oracle/operators.py:four_col_general). */
+int pt_gen_fourmat_general(int n, double period, int order, double* D, double* work,
+                           pt_stream_t stream);
 /* Fornberg finite-difference weights, one row per node, in banded row-start layout:
  * start[i] = clip(i - floor(w/2), 0, n - wmax) (periodic: i - floor(w/2), wrapped by the
  * kernels), W[i*wmax + s] multiplies x[start[i] + s].  w = 2*floor((order+1)/2) - 1 + accuracy

@@ -100,6 +100,45 @@ def cheb_mat(x, order=1):
     return D
 
 
+def bary_mat(x, order=1):
+    """Polynomial collocation differentiation matrix on ARBITRARY distinct nodes (what a
+    non-affine mapper of the reference produces, grid.py:201-207): barycentric weights
+    w_j = 1/prod_{k!=j}(x_j-x_k) (Berrut & Trefethen 2004), D1_ij = (w_j/w_i)/(x_i-x_j), higher
+    orders by the recursion of ``cheb_mat`` with c_i/c_j replaced by w_j/w_i.  The products are
+    kept as mantissa*2^exponent (frexp after every multiply) exactly as pt_gen_barymat does."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.size
+    mant = np.ones(n)
+    expo = np.zeros(n, dtype=np.int64)
+    for k in range(n):
+        f = x - x[k]
+        f[k] = 1.0
+        mant, ex = np.frexp(mant * f)
+        expo += ex
+    off = ~np.eye(n, dtype=bool)
+    cr = np.ldexp(mant[:, None] / mant[None, :], (expo[:, None] - expo[None, :]).astype(np.int32))
+    dx = np.where(off, x[:, None] - x[None, :], 1.0)
+    D = np.where(off, cr / dx, 0.0)
+    D[~off] = -_seq_row_sum(D)
+    for l in range(2, order + 1):
+        diag = np.diag(D).copy()
+        Dn = np.where(off, (l / dx) * (cr * diag[:, None] - D), 0.0)
+        Dn[~off] = -_seq_row_sum(Dn)
+        D = Dn
+    return D
+
+
+def is_affine_cgl(x, tol=1e-13):
+    """True when ``x`` is an affine image (either orientation) of the CGL set."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.size
+    if n < 2 or x[-1] == x[0]:
+        return False
+    t = (x - x[0]) / (x[-1] - x[0])
+    ref = (1.0 - np.cos(np.arange(n) * np.pi / (n - 1))) / 2.0
+    return bool(np.max(np.abs(t - ref)) <= tol)
+
+
 # --------------------------------------------------------------------------------------------
 # Fourier spectral (Trefethen 2000 ch. 3; Weideman & Reddy 2000 `fourdif`)
 # --------------------------------------------------------------------------------------------
@@ -138,9 +177,37 @@ def four_col(n, period, order):
     return col
 
 
+def four_col_general(n, period, order):
+    """First column for any order: (1/n) sum_k (i k s)^p exp(2 pi i k m / n) over the retained
+    modes |k| <= (n-1)/2, plus the Nyquist mode k = n/2 for even n and even order (it is dropped
+    for odd orders, as in the order-1 closed form).  Sequential summation in k."""
+    s = (2.0 * np.pi) / period
+    m = np.arange(n)
+    K = (n - 1) // 2
+    even_p = order % 2 == 0
+    sgn = (-1.0 if (order // 2) % 2 else 1.0) if even_p else (1.0 if ((order - 1) // 2) % 2 else -1.0)
+    acc = np.zeros(n)
+    for k in range(1, K + 1):
+        ks = k * s
+        pw = 1.0
+        for _ in range(order):
+            pw = pw * ks
+        frac = ((2 * k * m) % (2 * n)) / float(n)
+        trig = np.cos(np.pi * frac) if even_p else np.sin(np.pi * frac)
+        acc = acc + ((2.0 * sgn) * pw) * trig
+    if n % 2 == 0 and even_p:
+        ks = (n // 2) * s
+        pw = 1.0
+        for _ in range(order):
+            pw = pw * ks
+        acc = acc + (sgn * pw) * np.where(m % 2 == 1, -1.0, 1.0)
+    return acc / float(n)
+
+
 def four_mat(n, period, order=1):
-    """Dense circulant matrix D[i, j] = col[(i - j) mod n]."""
-    col = four_col(n, period, order)
+    """Dense circulant matrix D[i, j] = col[(i - j) mod n] (closed forms for orders 1 and 2,
+    direct summation of the symbol for higher orders)."""
+    col = four_col(n, period, order) if order in (1, 2) else four_col_general(n, period, order)
     i = np.arange(n)
     return col[(i[:, None] - i[None, :]) % n]
 

@@ -59,7 +59,9 @@ SIGNATURES = {
     "pt_grid_expand": (_c_i32, [_c_ptr, ctypes.POINTER(_c_i64), _c_i32, _c_i32, _c_ptr, _c_ptr]),
     "pt_grid_axpoints": (_c_i32, [_c_ptr, _c_i64, _c_i64, _c_ptr, _c_ptr]),
     "pt_gen_chebmat": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr]),
+    "pt_gen_barymat": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
     "pt_gen_fourmat": (_c_i32, [_c_i32, _c_f64, _c_i32, _c_ptr, _c_ptr]),
+    "pt_gen_fourmat_general": (_c_i32, [_c_i32, _c_f64, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
     "pt_gen_fornberg": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_f64, _c_ptr,
                                  _c_ptr, _c_i32, _c_ptr]),
     "pt_band_to_dense": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr]),

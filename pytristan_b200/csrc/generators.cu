@@ -148,6 +148,77 @@ __global__ void fourmat_kernel(int n, double s, int order, double* __restrict__ 
   D[idx] = four_col(k, n, s, order);
 }
 
+
+// ---- K6: polynomial collocation on arbitrary nodes (barycentric weights) -------------------------
+// w_j = 1 / prod_{k != j} (x_j - x_k) held as mantissa * 2^exponent (frexp after every multiply,
+// exact scaling) so that n = 2048 nodes on [-1, 1] neither under- nor overflow.
+__global__ void bary_weights_kernel(const double* __restrict__ x, int n, double* __restrict__ mant,
+                                    int* __restrict__ expo) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const double xj = x[j];
+  double m = 1.0;
+  int e = 0;
+  for (int k = 0; k < n; ++k) {
+    if (k == j) continue;
+    m = __dmul_rn(m, __dsub_rn(xj, x[k]));
+    int ex;
+    m = frexp(m, &ex);
+    e += ex;
+  }
+  mant[j] = m;   // prod = m * 2^e = 1 / w_j
+  expo[j] = e;
+}
+
+__global__ void bary_offdiag_kernel(const double* __restrict__ x, const double* __restrict__ mant,
+                                    const int* __restrict__ expo, int n, int l, double* D) {
+  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (idx >= int64_t(n) * n) return;
+  const int i = int(idx / n), j = int(idx % n);
+  if (i == j) return;
+  // w_j / w_i = prod_i / prod_j
+  const double cr = ldexp(__ddiv_rn(mant[i], mant[j]), expo[i] - expo[j]);
+  const double dx = __dsub_rn(x[i], x[j]);
+  if (l == 1) {
+    D[idx] = __ddiv_rn(cr, dx);
+  } else {
+    const double t = __dsub_rn(__dmul_rn(cr, D[int64_t(i) * n + i]), D[idx]);
+    D[idx] = __dmul_rn(__ddiv_rn(double(l), dx), t);
+  }
+}
+
+// ---- K6: Fourier, any order, by direct summation of the symbol (i k s)^p ----------------------------
+__global__ void four_general_kernel(int n, double s, int order, double* __restrict__ col) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  const int K = (n - 1) / 2;               // plain modes 1..K; n even adds the Nyquist mode n/2
+  const bool even_p = (order % 2) == 0;
+  const double sgn = even_p ? ((order / 2) % 2 ? -1.0 : 1.0) : (((order - 1) / 2) % 2 ? 1.0 : -1.0);
+  double acc = 0.0;
+  for (int k = 1; k <= K; ++k) {
+    double ks = __dmul_rn(double(k), s), pw = 1.0;
+    for (int q = 0; q < order; ++q) pw = __dmul_rn(pw, ks);
+    const long long r = (2LL * k * m) % (2LL * n);        // theta = pi * r / n, exact reduction
+    double sn, cs;
+    sincospi(__ddiv_rn(double(r), double(n)), &sn, &cs);
+    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(2.0 * sgn, pw), even_p ? cs : sn));
+  }
+  if ((n % 2) == 0 && even_p) {
+    double ks = __dmul_rn(double(n / 2), s), pw = 1.0;
+    for (int q = 0; q < order; ++q) pw = __dmul_rn(pw, ks);
+    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(sgn, pw), (m % 2) ? -1.0 : 1.0));
+  }
+  col[m] = __ddiv_rn(acc, double(n));
+}
+
+__global__ void circulant_kernel(const double* __restrict__ col, int n, double* __restrict__ D) {
+  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (idx >= int64_t(n) * n) return;
+  int k = int(idx / n) - int(idx % n);
+  if (k < 0) k += n;
+  D[idx] = col[k];
+}
+
 // ---- K6: Fornberg finite-difference weights --------------------------------------------------------
 constexpr int FD_MAXW = 16;
 constexpr int FD_MAXM = 6;
@@ -403,6 +474,23 @@ extern "C" int pt_gen_chebmat(const double* x, int n, int order, double* D, pt_s
   return pt::check_launch("pt_gen_chebmat");
 }
 
+
+extern "C" int pt_gen_barymat(const double* x, int n, int order, double* D, double* work,
+                              pt_stream_t stream) {
+  PT_REQUIRE(x && D && work, "pt_gen_barymat: null pointer");
+  PT_REQUIRE(n >= 2, "pt_gen_barymat: need at least 2 nodes, got %d", n);
+  PT_REQUIRE(order >= 1 && order <= 8, "pt_gen_barymat: order=%d outside [1,8]", order);
+  cudaStream_t st = pt::as_stream(stream);
+  double* mant = work;
+  int* expo = reinterpret_cast<int*>(work + n);
+  bary_weights_kernel<<<blocks_for(n, 64), 64, 0, st>>>(x, n, mant, expo);
+  for (int l = 1; l <= order; ++l) {
+    bary_offdiag_kernel<<<blocks_for(int64_t(n) * n, 256), 256, 0, st>>>(x, mant, expo, n, l, D);
+    cheb_diag_kernel<<<blocks_for(n, 64), 64, 0, st>>>(n, D);
+  }
+  return pt::check_launch("pt_gen_barymat");
+}
+
 extern "C" int pt_gen_fourmat(int n, double period, int order, double* D, pt_stream_t stream) {
   PT_REQUIRE(D, "pt_gen_fourmat: null pointer");
   PT_REQUIRE(n >= 2, "pt_gen_fourmat: need at least 2 nodes, got %d", n);
@@ -411,6 +499,19 @@ extern "C" int pt_gen_fourmat(int n, double period, int order, double* D, pt_str
   const double s = (2.0 * kPi) / period;
   fourmat_kernel<<<blocks_for(int64_t(n) * n, 256), 256, 0, pt::as_stream(stream)>>>(n, s, order, D);
   return pt::check_launch("pt_gen_fourmat");
+}
+
+extern "C" int pt_gen_fourmat_general(int n, double period, int order, double* D, double* work,
+                                      pt_stream_t stream) {
+  PT_REQUIRE(D && work, "pt_gen_fourmat_general: null pointer");
+  PT_REQUIRE(n >= 2, "pt_gen_fourmat_general: need at least 2 nodes, got %d", n);
+  PT_REQUIRE(order >= 1 && order <= 8, "pt_gen_fourmat_general: order=%d outside [1,8]", order);
+  PT_REQUIRE(period > 0.0, "pt_gen_fourmat_general: period must be positive");
+  const double s = (2.0 * kPi) / period;
+  cudaStream_t st = pt::as_stream(stream);
+  four_general_kernel<<<blocks_for(n, 64), 64, 0, st>>>(n, s, order, work);
+  circulant_kernel<<<blocks_for(int64_t(n) * n, 256), 256, 0, st>>>(work, n, D);
+  return pt::check_launch("pt_gen_fourmat_general");
 }
 
 extern "C" int pt_gen_fornberg(const double* x, int n, int order, int accuracy, int periodic,

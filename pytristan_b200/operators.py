@@ -86,6 +86,16 @@ def _is_uniform(x):
     return bool(np.max(np.abs(np.diff(x) - h)) <= tol)
 
 
+def _is_affine_cgl(x, tol=1e-13):
+    """True when the nodes are an affine image (either orientation) of the CGL set."""
+    n = x.size
+    if n < 2 or x[-1] == x[0]:
+        return False
+    t = (x - x[0]) / (x[-1] - x[0])
+    ref = (1.0 - np.cos(np.arange(n) * np.pi / (n - 1))) / 2.0
+    return bool(np.max(np.abs(t - ref)) <= tol)
+
+
 def _field_to_device(u):
     """(device tensor float64 contiguous, kind) where kind tells how to hand the result back."""
     torch = _lib.require_cuda()
@@ -294,31 +304,45 @@ class ChebMat(_DiffMat):
     """Chebyshev collocation differentiation matrix on a Chebyshev-Gauss-Lobatto axis (any affine
     map, either orientation — it is built from the axis' actual nodes).
 
-    ``ChebMat(grid, axis=0, order=1)``; ``grid`` may be a ``Grid``, a registered grid number or
-    a 1-D node array.  Entries: D1_ij = (c_i/c_j)/(x_i-x_j); higher orders by Welfert's
-    recursion; diagonals by the negative-sum trick.
+    ``ChebMat(grid, axis=0, order=1, weights="auto")``; ``grid`` may be a ``Grid``, a registered
+    grid number or a 1-D node array.  Entries: D1_ij = (c_i/c_j)/(x_i-x_j); higher orders by
+    Welfert's recursion; diagonals by the negative-sum trick.  Nodes that are not an affine image
+    of the CGL set (a custom stretching mapper) get the polynomial collocation matrix on the
+    actual nodes instead (barycentric weights, ``weights="bary"``).
     """
 
     _KIND = "cheb"
 
-    def __new__(cls, grid, axis=0, order=1):
+    def __new__(cls, grid, axis=0, order=1, weights="auto"):
         nodes, npts, axis, gnum = _resolve_axis(grid, axis)
         order = operator.index(order)
         if order < 1:
             raise ValueError("order must be a positive integer")
         if nodes.size < 2:
             raise ValueError("a Chebyshev axis needs at least 2 nodes")
+        if weights not in ("auto", "cgl", "bary"):
+            raise ValueError("weights must be 'auto', 'cgl' or 'bary'")
+        if weights == "auto":
+            weights = "cgl" if _is_affine_cgl(nodes) else "bary"
         lib = _lib.load()
         d_x = _lib.to_device(nodes)
         n = nodes.size
         d_mat = _lib.empty((n, n))
-        _lib.check(lib.pt_gen_chebmat(_lib.dptr(d_x), n, order, _lib.dptr(d_mat),
-                                      _lib.stream_ptr()), "pt_gen_chebmat")
-        return cls._wrap(d_mat, npts, axis, order, gnum)
+        if weights == "cgl":
+            _lib.check(lib.pt_gen_chebmat(_lib.dptr(d_x), n, order, _lib.dptr(d_mat),
+                                          _lib.stream_ptr()), "pt_gen_chebmat")
+        else:
+            # nodes from a non-affine mapper: polynomial collocation with barycentric weights
+            work = _lib.empty((2 * n,))
+            _lib.check(lib.pt_gen_barymat(_lib.dptr(d_x), n, order, _lib.dptr(d_mat), _lib.dptr(work),
+                                          _lib.stream_ptr()), "pt_gen_barymat")
+        obj = cls._wrap(d_mat, npts, axis, order, gnum)
+        obj.weights_kind = weights
+        return obj
 
 
 class FourMat(_DiffMat):
-    """Fourier spectral differentiation matrix (order 1 or 2) on an equispaced periodic axis
+    """Fourier spectral differentiation matrix (orders 1-8) on an equispaced periodic axis
     whose endpoint is excluded, e.g. the theta axis of ``get_polar_grid`` (reference
     grid.py:505).  ``period`` defaults to ``n * spacing``."""
 
@@ -327,8 +351,8 @@ class FourMat(_DiffMat):
     def __new__(cls, grid, axis=0, order=1, period=None):
         nodes, npts, axis, gnum = _resolve_axis(grid, axis)
         order = operator.index(order)
-        if order not in (1, 2):
-            raise ValueError("FourMat generates orders 1 and 2")
+        if not 1 <= order <= 8:
+            raise ValueError("FourMat generates orders 1 to 8")
         n = nodes.size
         if n < 2:
             raise ValueError("a Fourier axis needs at least 2 nodes")
@@ -338,8 +362,14 @@ class FourMat(_DiffMat):
             period = n * ((nodes[-1] - nodes[0]) / (n - 1))
         lib = _lib.load()
         d_mat = _lib.empty((n, n))
-        _lib.check(lib.pt_gen_fourmat(n, float(period), order, _lib.dptr(d_mat),
-                                      _lib.stream_ptr()), "pt_gen_fourmat")
+        if order <= 2:       # closed forms (Trefethen ch. 3)
+            _lib.check(lib.pt_gen_fourmat(n, float(period), order, _lib.dptr(d_mat),
+                                          _lib.stream_ptr()), "pt_gen_fourmat")
+        else:                # direct summation of the symbol (i k s)^p
+            work = _lib.empty((n,))
+            _lib.check(lib.pt_gen_fourmat_general(n, float(period), order, _lib.dptr(d_mat),
+                                                  _lib.dptr(work), _lib.stream_ptr()),
+                       "pt_gen_fourmat_general")
         obj = cls._wrap(d_mat, npts, axis, order, gnum)
         obj.period = float(period)
         return obj

@@ -394,3 +394,52 @@ def test_fused_gradient(npts, accuracy):
     band = oracle.findiff_band(oracle.cheb_nodes(npts[1], 0.0, 1.0), 1, accuracy)
     ref = oracle.stencil_apply(band, U, npts, 1)
     assert np.max(np.abs(got[1].cpu().numpy() - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+# ---------------------------------------------------------------------------------------------
+# collocation on non-affinely mapped nodes; Fourier orders > 2
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [9, 64, 257, 1024])
+@pytest.mark.parametrize("order", [1, 2])
+def test_barymat_entries(n, order):
+    import pytristan_b200 as pt
+
+    c = oracle.cheb_nodes(n)[::-1]
+    x = c + 0.15 * (1.0 - c * c)             # mildly stretched CGL nodes: monotone, not an affine image
+    assert not oracle.is_affine_cgl(x)
+    D = pt.ChebMat(x, order=order)
+    assert D.weights_kind == "bary"
+    ref = oracle.bary_mat(x, order)
+    scale = np.abs(ref).sum(axis=1, keepdims=True)
+    assert np.max(np.abs(np.asarray(D) - ref) / scale) <= 1e-14
+    # on true CGL nodes the barycentric matrix agrees with the c-pattern one
+    xc = oracle.cheb_nodes(n, 0.0, 2.0)
+    Db = pt.ChebMat(xc, order=order, weights="bary")
+    Dc = pt.ChebMat(xc, order=order)
+    assert Dc.weights_kind == "cgl"
+    sc = np.abs(np.asarray(Dc)).sum(axis=1, keepdims=True)
+    assert np.max(np.abs(np.asarray(Db) - np.asarray(Dc)) / sc) <= 2e-11     # two formulas, O(n eps) apart
+    # exact on polynomials of moderate degree (interpolation on stretched nodes is only as stable
+    # as the node distribution allows, so no claim is made for general smooth functions)
+    if order == 1:
+        p = np.polynomial.Polynomial([1.0, -2.0, 0.5, 3.0, -1.0])
+        assert np.max(np.abs(D @ p(x) - p.deriv(1)(x))) <= 1e-9 * np.abs(ref).sum(axis=1).max()
+
+
+@pytest.mark.parametrize("n", [8, 17, 64, 255])
+@pytest.mark.parametrize("order", [3, 4, 5])
+def test_fourmat_high_order(n, order):
+    import pytristan_b200 as pt
+
+    period = 2 * np.pi
+    x = -np.pi + period / n * np.arange(n)
+    D = pt.FourMat(x, order=order, period=period)
+    ref = oracle.four_mat(n, period, order)
+    assert np.max(np.abs(np.asarray(D) - ref)) <= 1e-12 * np.max(np.abs(ref))
+    if n >= 64:
+        f = np.exp(np.sin(x))
+        k = np.fft.fftfreq(n, 1.0 / n)
+        if n % 2 == 0 and order % 2 == 1:
+            k[n // 2] = 0.0
+        spec = np.real(np.fft.ifft((1j * k) ** order * np.fft.fft(f)))
+        assert np.max(np.abs(D @ f - spec)) <= 1e-12 * np.max(np.abs(ref) @ np.abs(f))     # relative to |D||f|

@@ -236,7 +236,7 @@ def test_operator_getter_validation():
     with pytest.raises(ValueError):
         pt.ChebMat(g, axis=0, order=0)
     with pytest.raises(ValueError):
-        pt.FourMat(g, axis=0, order=3)
+        pt.FourMat(g, axis=0, order=9)
     with pytest.raises(ValueError):
         pt.FinDiffMat(g, axis=0, order=1, accuracy=3)
     with pytest.raises(ValueError):

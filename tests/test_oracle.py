@@ -201,3 +201,39 @@ def test_axis_apply_equals_kron(npts, axis):
         assert np.allclose(oracle.stencil_apply(b, G[axis], npts, axis), 1.0, atol=1e-12)
         Dd = oracle.band_to_dense(b["start"], b["W"])
         assert np.allclose(oracle.stencil_apply(b, U, npts, axis), oracle.apply_along_axis(Dd, U, npts, axis), atol=1e-12)
+
+
+# -- barycentric collocation, general-order Fourier ---------------------------------------------------------------------
+@pytest.mark.parametrize("n", [8, 33, 200])
+def test_bary_mat(n):
+    xc = oracle.cheb_nodes(n, -1.0, 1.0)
+    D = oracle.bary_mat(xc, 1)
+    Dc = oracle.cheb_mat(xc, 1)
+    assert np.max(np.abs(D - Dc)) <= 1e-11 * np.max(np.abs(Dc))        # same matrix on CGL nodes
+    x = np.sort(np.random.default_rng(n).uniform(-1, 1, min(n, 24)))   # arbitrary nodes, moderate degree
+    p = np.polynomial.Polynomial(np.random.default_rng(1).standard_normal(len(x)))
+    for order in (1, 2, 3):
+        Dp = oracle.bary_mat(x, order)
+        assert np.max(np.abs(Dp @ p(x) - p.deriv(order)(x))) <= 1e-7 * max(1.0, np.max(np.abs(p.deriv(order)(x)))) * 10 ** order
+    assert oracle.is_affine_cgl(oracle.cheb_nodes(50, 2.0, 5.0)) and oracle.is_affine_cgl(oracle.cheb_nodes(50))
+    assert not oracle.is_affine_cgl(np.linspace(0, 1, 50))
+    big = oracle.cheb_nodes(2048)                                       # no under/overflow at n = 2048
+    assert np.all(np.isfinite(oracle.bary_mat(big, 1)))
+
+
+@pytest.mark.parametrize("n", [8, 17, 64])
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_four_general_vs_fft_and_closed_forms(n, order):
+    period = 3.0
+    col = oracle.four_col_general(n, period, order)
+    if order in (1, 2):
+        ref = oracle.four_col(n, period, order)
+        assert np.max(np.abs(col - ref)) <= 1e-12 * np.max(np.abs(ref)) * n
+    rng = np.random.default_rng(n)
+    f = rng.standard_normal(n)
+    k = np.fft.fftfreq(n, 1.0 / n) * (2 * np.pi / period)
+    if n % 2 == 0 and order % 2 == 1:
+        k[n // 2] = 0.0
+    spec = np.real(np.fft.ifft((1j * k) ** order * np.fft.fft(f)))
+    D = oracle.four_mat(n, period, order) if order > 2 else col[(np.arange(n)[:, None] - np.arange(n)[None, :]) % n]
+    assert np.max(np.abs(D @ f - spec)) <= 1e-11 * np.abs(D).sum(axis=1).max() * np.max(np.abs(f))
