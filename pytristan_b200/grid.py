@@ -26,6 +26,7 @@ from ._manager import ObjectManager
 __all__ = [
     "cheb",
     "Grid",
+    "DeviceGrid",
     "_get_grid_manager",
     "get_grid",
     "get_polar_grid",
@@ -95,6 +96,89 @@ def _expand_axes(axes, dtype):
     return out
 
 
+def _expand_axes_device(axes, dtype):
+    """Axis arrays -> ``(ndim, prod(npts))`` CUDA tensor in the Grid layout (no host copy)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    tdtype = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
+              np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32}.get(np.dtype(dtype))
+    if tdtype is None:
+        raise TypeError(f"DeviceGrid: unsupported coordinate dtype {dtype}")
+    ndim = len(axes)
+    npts = [int(a.shape[0]) for a in axes]
+    total = 1
+    for n in npts:
+        total *= n
+    out = torch.empty((ndim, total), dtype=tdtype, device="cuda")
+    if total:
+        flat = np.concatenate([np.ascontiguousarray(a, dtype=dtype) for a in axes])
+        d_axes = torch.from_numpy(flat).cuda()
+        c_npts = (ctypes.c_int64 * ndim)(*npts)
+        _lib.check(
+            lib.pt_grid_expand(_lib.dptr(d_axes), c_npts, ndim, np.dtype(dtype).itemsize, _lib.dptr(out),
+                               _lib.stream_ptr()),
+            "pt_grid_expand",
+        )
+    return out
+
+
+class DeviceGrid:
+    """Device-resident mesh with the Grid layout: ``tensor`` is a CUDA
+    ``(ndim, prod(npts))`` array with the same values, bit for bit, as ``Grid`` would hold, but it
+    is never copied to the host — this is how meshes the reference cannot materialise on a host
+    (1024^3: 24 GiB, ~72 GiB peak in reference grid.py:83-88) are built in milliseconds.
+
+    Same constructors and accessors as ``Grid`` (``from_bounds``, ``from_arrs``, ``axpoints``,
+    ``npts``, ``num_dim``, ``num``); operators accept it wherever they accept a ``Grid``.
+    """
+
+    def __init__(self, arrs):
+        axes = [np.asarray(a).ravel() for a in arrs]
+        if not axes:
+            raise ValueError("DeviceGrid needs at least one axis")
+        self._axes = [np.array(a) for a in axes]
+        self.npts = tuple(len(a) for a in axes)
+        self.num_dim = len(axes)
+        self._num = None
+        self.tensor = _expand_axes_device(axes, np.result_type(*axes))
+
+    @classmethod
+    def from_bounds(cls, *bounds, axes=[], mappers=[]):
+        return cls(Grid._axes_from_bounds(bounds, axes, mappers))
+
+    @classmethod
+    def from_arrs(cls, *arrs):
+        for arr in arrs:
+            if np.asarray(arr).ndim != 1:
+                raise ValueError("Coordinate arrays must be one-dimensional array-like.")
+        return cls(arrs)
+
+    @property
+    def num(self):
+        return self._num
+
+    @property
+    def shape(self):
+        return tuple(self.tensor.shape)
+
+    def axpoints(self, axis):
+        try:
+            operator.index(axis)
+        except TypeError as exc:
+            raise TypeError("Axis' index axis must be an integer.") from exc
+        if axis >= self.num_dim or axis < -self.num_dim:
+            raise IndexError(f"Axis' index {axis} out of bounds for the grid with {self.num_dim} dimensions.")
+        return np.array(self._axes[axis])
+
+    def to_host(self):
+        """The equivalent host ``Grid`` (copies ``ndim * prod(npts)`` elements)."""
+        return Grid(self._axes)
+
+    def __repr__(self):
+        tag = "no unique identifier" if self._num is None else f"unique identifier: {self._num}"
+        return f"Instance of {type(self).__name__} with {tag}."
+
+
 class Grid(np.ndarray):
     """Linearised N-D mesh: row ``i`` holds the coordinate along axis ``i`` of every grid point,
     points ordered with axis 0 fastest (column-major linearisation, reference grid.py:85-88).
@@ -124,7 +208,13 @@ class Grid(np.ndarray):
 
     @classmethod
     def from_bounds(cls, *bounds, axes=[], mappers=[]):
-        """Grid from ``(lower, upper, npts)`` triples, one per dimension.
+        """Grid from ``(lower, upper, npts)`` triples, one per dimension (see
+        ``_axes_from_bounds`` for the validation and error matrix)."""
+        return cls(cls._axes_from_bounds(bounds, axes, mappers))
+
+    @staticmethod
+    def _axes_from_bounds(bounds, axes, mappers):
+        """1-D axis arrays from ``(lower, upper, npts)`` triples, one per dimension.
 
         ``axes``/``mappers``: indices of the axes to map and the mapper for each, called as
         ``mapper(npts, lower, upper)``; unmapped axes use ``numpy.linspace``.
@@ -165,11 +255,10 @@ class Grid(np.ndarray):
                 )
             mapper_of = dict(zip(idx.tolist(), mappers))
 
-        arrs = tuple(
+        return tuple(
             mapper_of[k](bound[2], bound[0], bound[1]) if k in mapper_of else np.linspace(*bound)
             for k, bound in enumerate(bounds)
         )
-        return cls(arrs)
 
     @classmethod
     def from_arrs(cls, *arrs):
@@ -233,12 +322,13 @@ def _get_grid_manager(_grid_manager_instance=ObjectManager()):
     return _grid_manager_instance
 
 
-def get_grid(*args, from_bounds=False, axes=[], mappers=[], num=None, overwrite=False):
+def get_grid(*args, from_bounds=False, axes=[], mappers=[], num=None, overwrite=False, device=False):
     """Return the registered grid ``num`` or build, register and return a new one.
 
     ``args`` are 1-D coordinate arrays, or ``(lower, upper, npts)`` bounds when
     ``from_bounds=True``.  Without ``num`` the new grid gets ``max(existing) + 1`` (0 for an
-    empty registry).  ``overwrite=True`` rebuilds an existing identifier.
+    empty registry).  ``overwrite=True`` rebuilds an existing identifier.  ``device=True`` (an
+    extension) registers a ``DeviceGrid`` that lives on the GPU only.
 
     Raises TypeError for a non-integer ``num`` and ValueError when the grid does not exist and
     no data is given (reference grid.py:392-421).
@@ -257,11 +347,15 @@ def get_grid(*args, from_bounds=False, axes=[], mappers=[], num=None, overwrite=
     if grid is None or overwrite:
         if not args:
             raise ValueError("Could not create a new grid - no grid data supplied.")
+        kind = DeviceGrid if device else Grid
         if from_bounds:
-            grid = Grid.from_bounds(*args, axes=axes, mappers=mappers)
+            grid = kind.from_bounds(*args, axes=axes, mappers=mappers)
         else:
-            grid = Grid.from_arrs(*args)
-        grid.num = num
+            grid = kind.from_arrs(*args)
+        if device:
+            grid._num = num
+        else:
+            grid.num = num
         setattr(manager, str(num), grid)
     return grid
 

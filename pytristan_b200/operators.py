@@ -29,7 +29,7 @@ import numpy as np
 
 from . import _lib
 from ._manager import ObjectManager
-from .grid import Grid, _get_grid_manager
+from .grid import DeviceGrid, Grid, _get_grid_manager
 
 __all__ = [
     "ChebMat",
@@ -61,7 +61,7 @@ def _resolve_axis(grid, axis):
         if found is None:
             raise ValueError(f"No grid with identifier {grid} is registered.")
         grid = found
-    if isinstance(grid, Grid) and grid.npts is not None:
+    if isinstance(grid, DeviceGrid) or (isinstance(grid, Grid) and grid.npts is not None):
         try:
             operator.index(axis)
         except TypeError as exc:
@@ -534,7 +534,7 @@ def _get_mat_manager(kind, _managers={}):
 
 
 def _grid_number(grid):
-    if isinstance(grid, Grid):
+    if isinstance(grid, (Grid, DeviceGrid)):
         if grid.num is None:
             raise ValueError("the grid is not registered: create it with get_grid")
         return int(grid.num)
