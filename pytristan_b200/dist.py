@@ -125,9 +125,6 @@ class SlabStencil:
             r %= self.world
         elif r < 0 or r >= self.world:
             return 0
-        if r == self.rank and self.world == 1:
-            # single rank, periodic: the halo wraps onto itself
-            pass
         z0, z1 = shard_range(self.n, r, self.world)
         first = start[z0:z1]
         if upper:   # rank r sits below: it needs rows above its z1, i.e. this rank's first rows

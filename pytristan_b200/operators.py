@@ -471,9 +471,7 @@ class FinDiffMat(_DiffMat):
         return d_y
 
     def _matrix_product(self, d_u, cols):
-        torch = _lib.torch_mod()
-        n = int(self.shape[1])
-        return self._apply_device(d_u, 1, n, cols, None, 1.0, 0.0, None, None)
+        return self._apply_device(d_u, 1, int(self.shape[1]), cols, None, 1.0, 0.0, None, None)
 
 
 class PolarLaplacian:

@@ -443,3 +443,29 @@ def test_fourmat_high_order(n, order):
             k[n // 2] = 0.0
         spec = np.real(np.fft.ifft((1j * k) ** order * np.fft.fft(f)))
         assert np.max(np.abs(D @ f - spec)) <= 1e-12 * np.max(np.abs(ref) @ np.abs(f))     # relative to |D||f|
+
+
+# ---------------------------------------------------------------------------------------------
+# host-buffer pipeline (the e2e path of bench.py)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nfields,chunk", [(1, None), (7, 2), (16, None), (5, 8)])
+def test_apply_host_pipeline(nfields, chunk):
+    import pytristan_b200 as pt
+
+    torch = _torch()
+    g = pt.Grid.from_bounds((0.0, 2 * np.pi - 2 * np.pi / 48, 48), (-1.0, 1.0, 33), axes=[1], mappers=[pt.cheb])
+    ops = [pt.FourMat(g, axis=0, order=1), pt.ChebMat(g, axis=1, order=2), pt.FinDiffMat(g, axis=0, order=1, accuracy=4, periodic=True)]
+    rng = np.random.default_rng(1234)
+    U = rng.standard_normal((nfields, 48 * 33))
+    ref = [op.apply(U) for op in ops]
+    got = pt.apply_host(ops, U, chunk_fields=chunk)                      # ndarray in, ndarrays out
+    assert all(isinstance(a, np.ndarray) and np.array_equal(a, b) for a, b in zip(got, ref))
+    hin = torch.from_numpy(U).pin_memory()
+    houts = [torch.empty_like(hin).pin_memory() for _ in ops]
+    res = pt.apply_host(ops, hin, houts, chunk_fields=chunk)             # pinned tensors in and out
+    torch.cuda.synchronize()
+    assert all(r.data_ptr() == o.data_ptr() for r, o in zip(res, houts))
+    assert all(np.array_equal(o.numpy(), b) for o, b in zip(houts, ref))
+    assert pt.launches_per_apply(ops) == 3
+    with pytest.raises(ValueError):
+        pt.apply_host(ops, U.ravel()[:-1])
