@@ -18,126 +18,46 @@
 //
 // FP64 tensor cores on sm_100a are warp-level only (tcgen05 has no f64 kind), so accumulators
 // live in registers; see DESIGN.md §4.1 for the roofline this kernel is judged against.
-#include "common.cuh"
+#include "dense_common.cuh"
+
+using namespace ptdense;
 
 namespace {
 
-struct DenseParams {
-  const double* __restrict__ Dp;
-  const double* __restrict__ U;
-  double* __restrict__ Y;
-  const double* __restrict__ scale;
-  int n_out, n_in;
-  int MP, KP;            // padded rows of the packed operator, number of k-panels
-  int mt_per_block;      // m-tiles (8 rows) handled by one CTA
-  int m_blocks;
-  int64_t before;
-  int64_t NN;            // number of field columns: after*before (K1) or after (K2)
-  int64_t slab_in;       // n_in*before: distance between consecutive `a` slabs of U
-  int64_t slab_out;      // n_out*before
-  double alpha, beta;
-  int scale_mode;
-  int64_t scale_len;
-};
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
-  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+__device__ __forceinline__ unsigned smem_u32(const void* ptr) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(ptr));
 }
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
-  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
 }
 
-// WARPS_M x WARPS_N warps, each owning up to WM m-tiles x WN n-tiles of 8x8.
-template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16>
-struct Cfg {
-  static constexpr int NT = WARPS_M * WARPS_N * 32;
-  static constexpr int BM = WARPS_M * WM * 8;
-  static constexpr int BN = WARPS_N * WN * 8;
-  static constexpr int BK = BKP * 4;
-  static constexpr int A_STAGE = BKP * BM * 4;                     // doubles
-  static constexpr int PB = KCONTIG ? (BK + 4) : (BN + 4);          // pitch, = 4 mod 16
-  static constexpr int B_STAGE = KCONTIG ? BN * PB : BK * PB;       // doubles
-  static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr size_t SMEM = size_t(STAGES) * STAGE * sizeof(double);
-};
-
-
-// ---- per-warp compute over one staged k-chunk, specialised on the exact number of m-tiles (MT) the
-// warp owns.  Predicated-off DMMAs still occupy the tensor pipe for their full 16 cycles (measured:
-// ncu r01a), so a warp that owns fewer than WM tiles must branch to code that only issues its own.
-template <class C, int MT, int WMAX, int WN, bool KCONTIG>
-__device__ __forceinline__ void load_frags(const double* As, const double* Bs, int pp, double (&af)[WMAX],
-                                           double (&bf)[WN]) {
-#pragma unroll
-  for (int i = 0; i < MT; ++i) af[i] = As[(pp * C::BM + i * 8) * 4];
-#pragma unroll
-  for (int j = 0; j < WN; ++j) bf[j] = KCONTIG ? Bs[j * 8 * C::PB + pp * 4] : Bs[pp * 4 * C::PB + j * 8];
-}
-
-template <class C, int MT, int WMAX, int WN, int BKP, bool KCONTIG>
-__device__ __forceinline__ void compute_full(const double* As, const double* Bs, double (&acc)[WMAX][WN][2]) {
-  // software pipelined: fragments of panel pp+1 are loaded before the DMMAs of panel pp issue
-  double af[2][WMAX], bf[2][WN];
-  load_frags<C, MT, WMAX, WN, KCONTIG>(As, Bs, 0, af[0], bf[0]);
-#pragma unroll
-  for (int pp = 0; pp < BKP; ++pp) {
-    if (pp + 1 < BKP) load_frags<C, MT, WMAX, WN, KCONTIG>(As, Bs, pp + 1, af[(pp + 1) & 1], bf[(pp + 1) & 1]);
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-      for (int j = 0; j < WN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[pp & 1][i], bf[pp & 1][j]);
-  }
-}
-
-template <class C, int MT, int WMAX, int WN, bool KCONTIG>
-__device__ __forceinline__ void compute_partial(const double* As, const double* Bs, double (&acc)[WMAX][WN][2],
-                                                int npanels) {
-#pragma unroll 1
-  for (int pp = 0; pp < npanels; ++pp) {
-    double af[WMAX], bf[WN];
-    load_frags<C, MT, WMAX, WN, KCONTIG>(As, Bs, pp, af, bf);
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-      for (int j = 0; j < WN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-  }
-}
-
-template <class C, int MT, int WMAX, int WN, int BKP, bool KCONTIG>
-struct MtDispatch {
-  static __device__ __forceinline__ void full(int my_mt, const double* As, const double* Bs,
-                                              double (&acc)[WMAX][WN][2]) {
-    if (my_mt == MT) compute_full<C, MT, WMAX, WN, BKP, KCONTIG>(As, Bs, acc);
-    else MtDispatch<C, MT - 1, WMAX, WN, BKP, KCONTIG>::full(my_mt, As, Bs, acc);
-  }
-  static __device__ __forceinline__ void partial(int my_mt, const double* As, const double* Bs,
-                                                 double (&acc)[WMAX][WN][2], int npanels) {
-    if (my_mt == MT) compute_partial<C, MT, WMAX, WN, KCONTIG>(As, Bs, acc, npanels);
-    else MtDispatch<C, MT - 1, WMAX, WN, BKP, KCONTIG>::partial(my_mt, As, Bs, acc, npanels);
-  }
-};
-template <class C, int WMAX, int WN, int BKP, bool KCONTIG>
-struct MtDispatch<C, 0, WMAX, WN, BKP, KCONTIG> {
-  static __device__ __forceinline__ void full(int, const double*, const double*, double (&)[WMAX][WN][2]) {}
-  static __device__ __forceinline__ void partial(int, const double*, const double*, double (&)[WMAX][WN][2], int) {}
-};
-
-template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB>
+// ATMA: the operator panels of a chunk (packed, contiguous: rows*32 bytes each) are staged by the
+// bulk-copy engine (cp.async.bulk, SASS UBLKCP) issued by one thread and tracked by one mbarrier
+// per stage; the field tile keeps the per-thread 16-byte cp.async.
+template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB, bool ATMA>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
 dense_apply_kernel(const DenseParams p) {
   using C = Cfg<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16>;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * C::STAGE);
+  if (ATMA) {
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < STAGES; ++s)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(full_bar + s)));
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+  }
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -193,17 +113,40 @@ dense_apply_kernel(const DenseParams p) {
     b_r0 = tid / CPR2;  // first column served
   }
 
+  // operator panels of one chunk through the bulk-copy engine (one thread, one mbarrier per stage)
+  auto issue_panels = [&](int stage, int chunk) {
+    if (tid != 0) return;
+    const int kp0 = chunk * BKP;
+    const int npan = min(BKP, p.KP - kp0);
+    const unsigned bytes = unsigned(rows_blk) * 32u;
+    uint64_t* bar = full_bar + stage;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
+                 "r"(unsigned(npan) * bytes)
+                 : "memory");
+    double* As = smem + size_t(stage) * C::STAGE;
+    for (int pp = 0; pp < npan; ++pp)
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+              smem_u32(As + pp * C::BM * 4)),
+          "l"(p.Dp + (size_t(kp0 + pp) * p.MP + m0) * 4), "r"(bytes), "r"(smem_u32(bar))
+          : "memory");
+  };
+
   // generic (bounds-checked) loader: used for the chunk that crosses the end of the k range
   auto load_stage_edge = [&](int stage, int chunk) {
     double* As = smem + size_t(stage) * C::STAGE;
     double* Bs = As + C::A_STAGE;
     const int kp0 = chunk * BKP;
-    for (int idx = tid; idx < BKP * C::BM * 2; idx += C::NT) {
-      const int pp = idx / (C::BM * 2);
-      const int c = idx - pp * (C::BM * 2);
-      const bool ok = (kp0 + pp < p.KP) && ((c >> 1) < rows_blk);
-      const double* src = ok ? p.Dp + (size_t(kp0 + pp) * p.MP + m0) * 4 + c * 2 : p.Dp;
-      cp_async16(As + (pp * C::BM * 4) + c * 2, src, ok ? 16 : 0);
+    if (ATMA) {
+      issue_panels(stage, chunk);
+    } else {
+      for (int idx = tid; idx < BKP * C::BM * 2; idx += C::NT) {
+        const int pp = idx / (C::BM * 2);
+        const int c = idx - pp * (C::BM * 2);
+        const bool ok = (kp0 + pp < p.KP) && ((c >> 1) < rows_blk);
+        const double* src = ok ? p.Dp + (size_t(kp0 + pp) * p.MP + m0) * 4 + c * 2 : p.Dp;
+        cp_async16(As + (pp * C::BM * 4) + c * 2, src, ok ? 16 : 0);
+      }
     }
     const int k0 = kp0 * 4;
     if (!KCONTIG) {
@@ -268,16 +211,20 @@ dense_apply_kernel(const DenseParams p) {
     if ((chunk + 1) * C::BK > p.n_in) { load_stage_edge(stage, chunk); return; }
     double* As = smem + size_t(stage) * C::STAGE;
     double* Bs = As + C::A_STAGE;
+    if (ATMA) {
+      issue_panels(stage, chunk);
+    } else {
 #pragma unroll
-    for (int pp = 0; pp < BKP; ++pp)
+      for (int pp = 0; pp < BKP; ++pp)
 #pragma unroll
-      for (int sub = 0; sub < ASUB; ++sub) {
-        const bool ok = (a_ok >> sub) & 1u;
-        if ((C::BM * 2) % C::NT == 0 || ((a_in >> sub) & 1u))
-          cp_async16(As + pp * C::BM * 4 + (tid + sub * C::NT) * 2,
-                     ok ? a_ptr + pp * a_panel + sub * C::NT * 2 : p.Dp, ok ? 16 : 0);
-      }
-    a_ptr += BKP * a_panel;
+        for (int sub = 0; sub < ASUB; ++sub) {
+          const bool ok = (a_ok >> sub) & 1u;
+          if ((C::BM * 2) % C::NT == 0 || ((a_in >> sub) & 1u))
+            cp_async16(As + pp * C::BM * 4 + (tid + sub * C::NT) * 2,
+                       ok ? a_ptr + pp * a_panel + sub * C::NT * 2 : p.Dp, ok ? 16 : 0);
+        }
+      a_ptr += BKP * a_panel;
+    }
     constexpr int BR = KCONTIG ? C::BN / RPP2 : C::BK / RPP1;
     constexpr int RPP = KCONTIG ? RPP2 : RPP1;
 #pragma unroll
@@ -320,6 +267,7 @@ dense_apply_kernel(const DenseParams p) {
       if (nxt < nchunks) load_stage(nxt % STAGES, nxt);
       cp_async_commit();
     }
+    if (ATMA) mbar_wait(full_bar + kc % STAGES, unsigned(kc / STAGES) & 1u);
     const double* As = smem + size_t(kc % STAGES) * C::STAGE + a_off;
     const double* Bs = smem + size_t(kc % STAGES) * C::STAGE + C::A_STAGE + b_off;
     if (kc < nfull) MtDispatch<C, WM, WM, WN, BKP, KCONTIG>::full(my_mt, As, Bs, acc);
@@ -393,15 +341,16 @@ __global__ void pack_operator_kernel(const double* __restrict__ D, int n_out, in
   }
 }
 
-template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB = 1>
+template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB = 1, bool ATMA = false>
 int launch_cfg(DenseParams& p, cudaStream_t stream) {
   using C = Cfg<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16>;
-  auto kern = dense_apply_kernel<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16, MINB>;
+  auto kern = dense_apply_kernel<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16, MINB, ATMA>;
+  constexpr size_t SMEM_BYTES = C::SMEM + (ATMA ? STAGES * sizeof(uint64_t) : 0);
   static bool attr_set[64] = {false};
   int dev = 0;
   PT_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
+    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
     attr_set[dev] = true;
   }
   const int mtiles = p.MP / 8;
@@ -413,20 +362,28 @@ int launch_cfg(DenseParams& p, cudaStream_t stream) {
   const int64_t grid = n_blocks * p.m_blocks;
   if (grid <= 0) return PT_OK;
   if (grid > 2147483647LL) return pt::fail(PT_ERR_UNSUPPORTED, "pt_dense_apply: grid too large");
-  kern<<<unsigned(grid), C::NT, C::SMEM, stream>>>(p);
+  kern<<<unsigned(grid), C::NT, SMEM_BYTES, stream>>>(p);
   return pt::check_launch("pt_dense_apply");
 }
 
 int g_dense_config = -1;  // tuning hook (pt_debug_set_dense_config); -1 = choose by shape
+int g_dense_atma = 0;     // tuning hook (pt_debug_set_dense_tma(2)): operator panels via cp.async.bulk
+int g_dense_tma = 0;      // tuning hook (pt_debug_set_dense_tma): 1 = persistent TMA/mbarrier kernel
+
+int choose_config(const DenseParams& p) {
+  if (g_dense_config >= 0) return g_dense_config;
+  // measured on B200 (tools/sweep_dense.py, profiles/r01_dense_config_sweep.md): the 96x64 tile
+  // with 3 CTAs/SM wins everywhere except when n_out is a large multiple of 128, where the
+  // 128x64 tile with 2 CTAs/SM has no ragged last block and slightly better operand reuse
+  return (p.n_out >= 1024 && p.n_out % 128 == 0) ? 5 : 9;
+}
 
 template <bool KCONTIG, bool VEC16>
 int launch_shape(DenseParams& p, cudaStream_t stream) {
-  int cfg = g_dense_config;
-  if (cfg < 0) {
-    // measured on B200 (tools/sweep_dense.py, profiles/r01_dense_config_sweep.md): the 96x64 tile
-    // with 3 CTAs/SM wins everywhere except when n_out is a large multiple of 128, where the
-    // 128x64 tile with 2 CTAs/SM has no ragged last block and slightly better operand reuse
-    cfg = (p.n_out >= 1024 && p.n_out % 128 == 0) ? 5 : 9;
+  const int cfg = choose_config(p);
+  if (g_dense_atma) {
+    if (cfg == 5) return launch_cfg<2, 2, 8, 4, 4, 4, KCONTIG, VEC16, 2, true>(p, stream);
+    return launch_cfg<1, 4, 12, 2, 4, 3, KCONTIG, VEC16, 3, true>(p, stream);
   }
   switch (cfg) {
     case 5: return launch_cfg<2, 2, 8, 4, 4, 4, KCONTIG, VEC16, 2>(p, stream);   // 64x32 per warp, 128x64 CTA, 2 CTAs/SM
@@ -437,6 +394,16 @@ int launch_shape(DenseParams& p, cudaStream_t stream) {
 inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
 
 }  // namespace
+
+namespace ptdense {
+int launch_tma(DenseParams& p, bool kcontig, int cfg, cudaStream_t stream);
+}
+
+extern "C" int pt_debug_set_dense_tma(int mode) {
+  g_dense_tma = (mode == 1);   // 1: persistent mbarrier kernel
+  g_dense_atma = (mode == 2);  // 2: cp.async kernel with bulk-copied operator panels
+  return PT_OK;
+}
 
 extern "C" int pt_debug_set_dense_config(int id) {
   g_dense_config = id;
@@ -496,9 +463,17 @@ extern "C" int pt_dense_apply(const double* packed, int n_out, int n_in, const d
   cudaStream_t st = pt::as_stream(stream);
   if (before == 1) {
     const bool vec = (n_in % 2 == 0) && aligned16(U);
+    if (vec && g_dense_tma) {
+      const int rc = ptdense::launch_tma(p, true, choose_config(p), st);
+      if (rc != PT_ERR_UNSUPPORTED) return rc;
+    }
     return vec ? launch_shape<true, true>(p, st) : launch_shape<true, false>(p, st);
   }
   const bool vec = (before % 2 == 0) && aligned16(U) && aligned16(Y);
+  if (vec && g_dense_tma) {
+    const int rc = ptdense::launch_tma(p, false, choose_config(p), st);
+    if (rc != PT_ERR_UNSUPPORTED) return rc;
+  }
   return vec ? launch_shape<false, true>(p, st) : launch_shape<false, false>(p, st);
 }
 

@@ -469,3 +469,34 @@ def test_apply_host_pipeline(nfields, chunk):
     assert pt.launches_per_apply(ops) == 3
     with pytest.raises(ValueError):
         pt.apply_host(ops, U.ravel()[:-1])
+
+
+# ---------------------------------------------------------------------------------------------
+# alternative staging paths of the dense kernel (bulk-copy engine / mbarrier pipeline)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [1, 2])
+def test_dense_bulk_copy_variants_bitwise(mode):
+    """mode 1: persistent kernel, mbarrier pipeline, operator panels via cp.async.bulk;
+    mode 2: default kernel with bulk-copied operator panels.  Same tiles and summation order as
+    the default cp.async kernel, so results must be bit-identical."""
+    import ctypes
+
+    from pytristan_b200 import _lib
+    from pytristan_b200.operators import _DiffMat
+
+    torch = _torch()
+    lib = _lib.load()
+    lib.pt_debug_set_dense_tma.argtypes = [ctypes.c_int]
+    try:
+        for npts, axis, batch in [((130, 64), 0, 3), ((64, 136), 1, 3), ((258, 40), 0, 1), ((40, 258), 1, 2), ((1024, 66), 0, 1), ((64, 2048), 1, 1)]:
+            n = npts[axis]
+            gen = torch.Generator(device="cuda").manual_seed(n)
+            op = _DiffMat._wrap(torch.randn(n, n, dtype=torch.float64, device="cuda", generator=gen), npts, axis, 1, None)
+            U = torch.randn(batch, int(np.prod(npts)), dtype=torch.float64, device="cuda", generator=gen)
+            lib.pt_debug_set_dense_tma(0)
+            y0 = op.apply(U)
+            lib.pt_debug_set_dense_tma(mode)
+            y1 = op.apply(U)
+            assert torch.equal(y0, y1), (mode, npts, axis)
+    finally:
+        lib.pt_debug_set_dense_tma(0)

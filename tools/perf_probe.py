@@ -58,6 +58,20 @@ def stencil(npts, axis, batch, label, order=1, acc=6):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "tma":
+        import ctypes
+        lib = _lib.load()
+        for on in (0, 2):
+            lib.pt_debug_set_dense_tma(ctypes.c_int(on))
+            print("== tma", on)
+            dense((1024, 257), 0, 64, "cfg2 d/dx K2 n=1024")
+            dense((1024, 257), 1, 64, "cfg2 d2/dy2 K1 n=257")
+            dense((1024, 512), 1, 16, "cfg3 radial K1 n=512")
+            dense((8192, 2048), 1, 1, "cfg5a-1/8 K1 n=2048")
+            dense((512, 512, 512), 0, 1, "cfg5b x K2 n=512")
+            dense((512, 512, 512), 1, 1, "cfg5b y K1 n=512")
+            dense((64, 4096), 0, 1, "K2 n=64")
+        lib.pt_debug_set_dense_tma(ctypes.c_int(0))
     if what == "tune":
         lib = _lib.load()
         lib.pt_debug_set_dense_config.argtypes = [__import__("ctypes").c_int]
