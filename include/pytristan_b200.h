@@ -167,6 +167,60 @@ int pt_stencil_grad3(const double* U, double* GX, double* GY, double* GZ, int nx
 int pt_permute3d(const double* in, double* out, int64_t d2, int64_t d1, int64_t d0, int perm,
                  pt_stream_t stream);
 
+/* ---- multi-GPU over peer memory (one process per GPU, one NVSwitch box) --------- */
+#define PT_IPC_HANDLE_BYTES 64
+/* Exchange buffer: plain device allocation (IPC-exportable), zero filled. */
+int pt_peer_alloc(int64_t bytes, void** ptr);
+int pt_peer_free(void* ptr);
+/* CUDA IPC handle of an exchange buffer (PT_IPC_HANDLE_BYTES bytes, moved between the ranks by
+ * the host, e.g. torch.distributed.all_gather_object) and its mapping in another process. */
+int pt_ipc_export(const void* ptr, void* handle64);
+int pt_ipc_open(const void* handle64, void** ptr);
+int pt_ipc_close(void* ptr);
+/* Device-side barrier among nranks processes.  flags is a DEVICE array of nranks pointers,
+ * flags[r] = rank r's flag array (nranks uint64 slots, zero initialised, peer mapped).  The kernel
+ * stores `epoch` (strictly increasing, >= 1) into slot `rank` of every peer and waits until
+ * every slot of its own array reached it: work enqueued before the barrier on any rank is
+ * visible to work enqueued after it on every rank.  timeout_ns > 0 bounds the wait; on expiry
+ * *status (device int, may be NULL) is set to 1 + the missing rank and the kernel returns. */
+int pt_peer_barrier(uint64_t* const* flags, int rank, int nranks, uint64_t epoch,
+                    int64_t timeout_ns, int* status, pt_stream_t stream);
+
+/* Where the elements of a locally held (after, n, before) array go in a pencil redistribution:
+ * element (a, i, b) -> base[i / chunk] + offset + (a / a_inner)*s_outer + (a % a_inner)*s_inner
+ *                      + (i % chunk)*s_i + b      (all strides in doubles).
+ * base is a DEVICE array of nranks peer-mapped buffers. */
+typedef struct pt_scatter_map {
+  int nranks;
+  int chunk;
+  int64_t a_inner, s_outer, s_inner, s_i, offset;
+  double* const* base;
+} pt_scatter_map;
+
+/* pt_dense_apply whose epilogue is the redistribution: alpha * (D @ U[a,:,b]) + beta * C[a,:,b]
+ * is stored through `map` straight into the buffers of the ranks that own it afterwards (K7 + C1
+ * fused: the NVLink transfer proceeds tile by tile under the DMMA main loop).  C (local, laid
+ * out like the un-scattered result (after, n_out, before)) may be NULL when beta == 0. */
+int pt_dense_apply_scatter(const double* packed, int n_out, int n_in, const double* U,
+                           const double* C, int64_t after, int64_t before, double alpha,
+                           double beta, const pt_scatter_map* map, pt_stream_t stream);
+/* The same redistribution for an array that is only moved (the field itself): 16-byte peer
+ * stores, no staging buffer, no pack/unpack pass.  before == 1 requires s_i == 1. */
+int pt_peer_scatter(const double* src, int n, int64_t after, int64_t before,
+                    const pt_scatter_map* map, pt_stream_t stream);
+
+/* pt_stencil_apply along a slab-sharded axis WITHOUT a halo exchange: the halo_lo rows below and
+ * the halo_hi rows above the n_own local rows are loaded from the neighbours' memory (U_lo points
+ * at the first needed row of the lower neighbour, U_hi at the first row of the upper one;
+ * lo_stride / hi_stride = doubles between consecutive slabs `a` there).  start[] (one entry per
+ * output row) is relative to the virtual slab halo_lo + n_own + halo_hi, as in
+ * pt_stencil_apply_ex with shift = halo_lo.  before must be > 1. */
+int pt_stencil_apply_halo(const double* W, const int32_t* start, int wmax, int n_own, int halo_lo,
+                          int halo_hi, const double* U, const double* U_lo, int64_t lo_stride,
+                          const double* U_hi, int64_t hi_stride, double* Y, int64_t after,
+                          int64_t before, const pt_uniform_rows* uni, double alpha, double beta,
+                          pt_stream_t stream);
+
 /* ---- measurement helper ------------------------------------------------------------------ */
 /* Register-resident DMMA loop: the FP64 tensor-core roofline denominator measured on the box.
  * Writes achieved TFLOP/s to *tflops_host. */

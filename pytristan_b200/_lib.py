@@ -27,6 +27,13 @@ class UniformRows(ctypes.Structure):
                 ("start_bnd", ctypes.POINTER(_c_i32))]
 
 
+class ScatterMap(ctypes.Structure):
+    """struct pt_scatter_map (include/pytristan_b200.h)."""
+
+    _fields_ = [("nranks", _c_i32), ("chunk", _c_i32), ("a_inner", _c_i64), ("s_outer", _c_i64),
+                ("s_inner", _c_i64), ("s_i", _c_i64), ("offset", _c_i64), ("base", _c_ptr)]
+
+
 def uniform_rows(band, n_out):
     """Build the pt_uniform_rows argument from a band dict (keys w, lo, hi, wuni, wmax, start,
     weights); returns None for non-uniform bands.  The arrays are kept alive on the struct."""
@@ -79,6 +86,18 @@ SIGNATURES = {
                                   ctypes.POINTER(ctypes.POINTER(UniformRows)), _c_ptr]),
     "pt_permute3d": (_c_i32, [_c_ptr, _c_ptr, _c_i64, _c_i64, _c_i64, _c_i32, _c_ptr]),
     "pt_measure_dmma_peak": (_c_i32, [ctypes.POINTER(_c_f64), _c_i32]),
+    "pt_peer_alloc": (_c_i32, [_c_i64, ctypes.POINTER(_c_ptr)]),
+    "pt_peer_free": (_c_i32, [_c_ptr]),
+    "pt_ipc_export": (_c_i32, [_c_ptr, _c_ptr]),
+    "pt_ipc_open": (_c_i32, [_c_ptr, ctypes.POINTER(_c_ptr)]),
+    "pt_ipc_close": (_c_i32, [_c_ptr]),
+    "pt_peer_barrier": (_c_i32, [_c_ptr, _c_i32, _c_i32, ctypes.c_uint64, _c_i64, _c_ptr, _c_ptr]),
+    "pt_dense_apply_scatter": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64,
+                                        _c_f64, ctypes.POINTER(ScatterMap), _c_ptr]),
+    "pt_peer_scatter": (_c_i32, [_c_ptr, _c_i32, _c_i64, _c_i64, ctypes.POINTER(ScatterMap), _c_ptr]),
+    "pt_stencil_apply_halo": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64,
+                                       _c_ptr, _c_i64, _c_ptr, _c_i64, _c_i64, ctypes.POINTER(UniformRows),
+                                       _c_f64, _c_f64, _c_ptr]),
 }
 
 SCALE_NONE, SCALE_ROW, SCALE_AFTER, SCALE_BEFORE = 0, 1, 2, 3

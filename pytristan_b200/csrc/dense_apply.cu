@@ -44,7 +44,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 // ATMA: the operator panels of a chunk (packed, contiguous: rows*32 bytes each) are staged by the
 // bulk-copy engine (cp.async.bulk, SASS UBLKCP) issued by one thread and tracked by one mbarrier
 // per stage; the field tile keeps the per-thread 16-byte cp.async.
-template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB, bool ATMA>
+// SCAT: the epilogue stores each output element straight into the buffer of the rank that owns it
+// after the pencil redistribution (peer memory over NVLink) instead of into a local Y.
+template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB, bool ATMA,
+          bool SCAT>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
 dense_apply_kernel(const DenseParams p) {
   using C = Cfg<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16>;
@@ -297,8 +300,14 @@ dense_apply_kernel(const DenseParams p) {
       s0 *= p.scale[b0];
       if (two) s1 *= p.scale[b1];
     }
-    double* y0 = p.Y + a0 * p.slab_out + b0;
-    double* y1 = p.Y + a1 * p.slab_out + b1;
+    // local addresses (Y, or the beta input C of the scatter form) and destination column offsets
+    const int64_t l0 = a0 * p.slab_out + b0, l1 = a1 * p.slab_out + b1;
+    int64_t d0 = 0, d1 = 0;
+    if (SCAT) {
+      const int64_t q0 = a0 / p.sc.a_inner, q1 = a1 / p.sc.a_inner;
+      d0 = p.sc.offset + q0 * p.sc.s_outer + (a0 - q0 * p.sc.a_inner) * p.sc.s_inner + b0;
+      d1 = p.sc.offset + q1 * p.sc.s_outer + (a1 - q1 * p.sc.a_inner) * p.sc.s_inner + b1;
+    }
 #pragma unroll
     for (int i = 0; i < WM; ++i) {
       if (i >= my_mt) continue;
@@ -309,17 +318,26 @@ dense_apply_kernel(const DenseParams p) {
       double v0 = r0 * acc[i][j][0];
       double v1 = r1 * acc[i][j][1];
       const int64_t off = int64_t(row) * p.before;
+      const double* c0 = (SCAT ? p.C : p.Y) + l0 + off;
+      const double* c1 = (SCAT ? p.C : p.Y) + l1 + off;
+      double *y0, *y1;
+      if (SCAT) {
+        const int dq = row / p.sc.chunk;
+        double* db = p.sc.base[dq] + int64_t(row - dq * p.sc.chunk) * p.sc.s_i;
+        y0 = db + d0; y1 = db + d1;
+      } else {
+        y0 = p.Y + l0 + off; y1 = p.Y + l1 + off;
+      }
       if (!KCONTIG && VEC16) {
         // before is even and nn is even: both columns are adjacent in the same slab
-        double2* dst = reinterpret_cast<double2*>(y0 + off);
-        if (use_beta) { const double2 o = *dst; v0 += p.beta * o.x; v1 += p.beta * o.y; }
-        *dst = make_double2(v0, v1);
+        if (use_beta) { const double2 o = *reinterpret_cast<const double2*>(c0); v0 += p.beta * o.x; v1 += p.beta * o.y; }
+        *reinterpret_cast<double2*>(y0) = make_double2(v0, v1);
       } else {
-        if (use_beta) v0 += p.beta * y0[off];
-        y0[off] = v0;
+        if (use_beta) v0 += p.beta * *c0;
+        *y0 = v0;
         if (two) {
-          if (use_beta) v1 += p.beta * y1[off];
-          y1[off] = v1;
+          if (use_beta) v1 += p.beta * *c1;
+          *y1 = v1;
         }
       }
     }
@@ -341,10 +359,11 @@ __global__ void pack_operator_kernel(const double* __restrict__ D, int n_out, in
   }
 }
 
-template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB = 1, bool ATMA = false>
+template <int WARPS_M, int WARPS_N, int WM, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB = 1, bool ATMA = false,
+          bool SCAT = false>
 int launch_cfg(DenseParams& p, cudaStream_t stream) {
   using C = Cfg<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16>;
-  auto kern = dense_apply_kernel<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16, MINB, ATMA>;
+  auto kern = dense_apply_kernel<WARPS_M, WARPS_N, WM, WN, BKP, STAGES, KCONTIG, VEC16, MINB, ATMA, SCAT>;
   constexpr size_t SMEM_BYTES = C::SMEM + (ATMA ? STAGES * sizeof(uint64_t) : 0);
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -378,9 +397,13 @@ int choose_config(const DenseParams& p) {
   return (p.n_out >= 1024 && p.n_out % 128 == 0) ? 5 : 9;
 }
 
-template <bool KCONTIG, bool VEC16>
+template <bool KCONTIG, bool VEC16, bool SCAT = false>
 int launch_shape(DenseParams& p, cudaStream_t stream) {
   const int cfg = choose_config(p);
+  if (SCAT) {
+    if (cfg == 5) return launch_cfg<2, 2, 8, 4, 4, 4, KCONTIG, VEC16, 2, false, SCAT>(p, stream);
+    return launch_cfg<1, 4, 12, 2, 4, 3, KCONTIG, VEC16, 3, false, SCAT>(p, stream);
+  }
   if (g_dense_atma) {
     if (cfg == 5) return launch_cfg<2, 2, 8, 4, 4, 4, KCONTIG, VEC16, 2, true>(p, stream);
     return launch_cfg<1, 4, 12, 2, 4, 3, KCONTIG, VEC16, 3, true>(p, stream);
@@ -449,7 +472,8 @@ extern "C" int pt_dense_apply(const double* packed, int n_out, int n_in, const d
   if (after == 0) return PT_OK;
 
   DenseParams p;
-  p.Dp = packed; p.U = U; p.Y = Y; p.scale = scale;
+  p.Dp = packed; p.U = U; p.Y = Y; p.C = Y; p.scale = scale;
+  p.sc = ScatterDev{nullptr, 1, 1, 0, 0, 0, 0};
   p.n_out = n_out; p.n_in = n_in;
   p.MP = 8 * ((n_out + 7) / 8);
   p.KP = (n_in + 3) / 4;
@@ -475,6 +499,43 @@ extern "C" int pt_dense_apply(const double* packed, int n_out, int n_in, const d
     if (rc != PT_ERR_UNSUPPORTED) return rc;
   }
   return vec ? launch_shape<false, true>(p, st) : launch_shape<false, false>(p, st);
+}
+
+// ---- dense apply fused with the pencil redistribution (scatter epilogue over peer memory) -------
+extern "C" int pt_dense_apply_scatter(const double* packed, int n_out, int n_in, const double* U,
+                                      const double* C, int64_t after, int64_t before, double alpha,
+                                      double beta, const pt_scatter_map* map, pt_stream_t stream) {
+  PT_REQUIRE(packed && U && map && map->base, "pt_dense_apply_scatter: null pointer");
+  PT_REQUIRE(n_out > 0 && n_in > 0, "pt_dense_apply_scatter: bad operator shape %d x %d", n_out, n_in);
+  PT_REQUIRE(after >= 0 && before >= 1, "pt_dense_apply_scatter: bad field shape");
+  PT_REQUIRE(map->nranks >= 1 && map->chunk >= 1 && int64_t(map->chunk) * map->nranks >= n_out,
+             "pt_dense_apply_scatter: %d destinations x %d rows do not cover n_out=%d", map->nranks,
+             map->chunk, n_out);
+  PT_REQUIRE(map->a_inner >= 1, "pt_dense_apply_scatter: a_inner must be >= 1");
+  PT_REQUIRE(beta == 0.0 || C != nullptr, "pt_dense_apply_scatter: beta != 0 needs C");
+  if (after == 0) return PT_OK;
+  DenseParams p;
+  p.Dp = packed; p.U = U; p.Y = nullptr; p.C = C ? C : U; p.scale = nullptr;
+  p.sc = ScatterDev{map->base, map->chunk, map->a_inner, map->s_outer, map->s_inner, map->s_i, map->offset};
+  p.n_out = n_out; p.n_in = n_in;
+  p.MP = 8 * ((n_out + 7) / 8);
+  p.KP = (n_in + 3) / 4;
+  p.before = before;
+  p.NN = after * before;
+  p.slab_in = int64_t(n_in) * before;
+  p.slab_out = int64_t(n_out) * before;
+  p.alpha = alpha; p.beta = beta;
+  p.scale_mode = PT_SCALE_NONE; p.scale_len = 1;
+  p.m_blocks = 1; p.mt_per_block = 1;
+  cudaStream_t st = pt::as_stream(stream);
+  if (before == 1) {
+    const bool vec = (n_in % 2 == 0) && aligned16(U);
+    return vec ? launch_shape<true, true, true>(p, st) : launch_shape<true, false, true>(p, st);
+  }
+  // 16-byte destination stores need every destination offset to be even (bases are 256-byte aligned)
+  const bool even = !((map->s_outer | map->s_inner | map->s_i | map->offset) & 1);
+  const bool vec = (before % 2 == 0) && aligned16(U) && (C == nullptr || aligned16(C)) && even;
+  return vec ? launch_shape<false, true, true>(p, st) : launch_shape<false, false, true>(p, st);
 }
 
 // ---- FP64 tensor-core peak (roofline denominator) ----------------------------------------------

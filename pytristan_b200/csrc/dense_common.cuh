@@ -5,11 +5,22 @@
 
 namespace ptdense {
 
+// Destination map of the scatter epilogue (pt_dense_apply_scatter): output element (a, i, b) is
+// stored at base[i / chunk] + offset + (a / a_inner)*s_outer + (a % a_inner)*s_inner
+// + (i % chunk)*s_i + b, where base[] are peer-mapped buffers of the ranks of a pencil row/column.
+struct ScatterDev {
+  double* const* base;
+  int chunk;
+  int64_t a_inner, s_outer, s_inner, s_i, offset;
+};
+
 struct DenseParams {
   const double* __restrict__ Dp;
   const double* __restrict__ U;
   double* __restrict__ Y;
+  const double* __restrict__ C;   // beta input of the scatter epilogue (local, laid out like Y)
   const double* __restrict__ scale;
+  ScatterDev sc;
   int n_out, n_in;
   int MP, KP;            // padded rows of the packed operator, number of k-panels
   int mt_per_block;      // m-tiles (8 rows) handled by one CTA

@@ -42,7 +42,23 @@ struct StencilParams {
   int periodic;
   int lo, hi;  // canonical interior rows [lo, hi) (fast kernels); table rows elsewhere
   double alpha, beta;
+  // peer-halo form (pt_stencil_apply_halo): the input slab is virtual — halo_lo rows read from Ulo
+  // (the lower neighbour's memory), then the n - halo_lo - halo_hi own rows of U, then halo_hi rows
+  // from Uhi.  lo_stride / hi_stride: distance between consecutive slabs `a` in those buffers.
+  const double* __restrict__ Ulo;
+  const double* __restrict__ Uhi;
+  int halo_lo, halo_hi;
+  int64_t lo_stride, hi_stride;
 };
+
+// address of (slab a, virtual input row j, column 0) in the peer-halo form
+__device__ __forceinline__ const double* halo_row(const StencilParams& p, int64_t a, int j) {
+  const int n_own = p.n - p.halo_lo - p.halo_hi;
+  if (j < p.halo_lo) return p.Ulo + a * p.lo_stride + int64_t(j) * p.before;
+  j -= p.halo_lo;
+  if (j < n_own) return p.U + (a * n_own + j) * p.before;
+  return p.Uhi + a * p.hi_stride + int64_t(j - n_own) * p.before;
+}
 
 __device__ __forceinline__ int wrap_index(int j, int n) {
   j %= n;
@@ -61,6 +77,13 @@ __device__ __forceinline__ double table_point(const StencilParams& p, const doub
   }
   return acc;
 }
+__device__ __forceinline__ double table_point_halo(const StencilParams& p, int64_t a, int64_t b, int i) {
+  const double* w = p.W + int64_t(i) * p.wmax;
+  const int s0 = p.start[i];
+  double acc = 0.0;
+  for (int s = 0; s < p.wmax; ++s) acc = fma(w[s], halo_row(p, a, s0 + s)[b], acc);
+  return acc;
+}
 
 __device__ __forceinline__ void store_point(const StencilParams& p, double* y, double v) {
   v *= p.alpha;
@@ -70,6 +93,7 @@ __device__ __forceinline__ void store_point(const StencilParams& p, double* y, d
 
 // ---- generic table kernel ------------------------------------------------------------------------
 // output rows i outside [skip_lo, skip_hi) of every slab; start[i] is relative to the input slab
+template <bool HALO>
 __global__ void __launch_bounds__(256) stencil_table_kernel(const StencilParams p, int skip_lo,
                                                              int skip_hi) {
   // rows that need the table per slab: i in [0, skip_lo) U [skip_hi, n)
@@ -82,8 +106,8 @@ __global__ void __launch_bounds__(256) stencil_table_kernel(const StencilParams 
     const int ii = int(r % per_slab);
     const int64_t a = r / per_slab;
     const int i = ii < skip_lo ? ii : ii - skip_lo + skip_hi;
-    const double* base = p.U + a * int64_t(p.n) * p.before + b;
-    const double v = table_point(p, base, i);
+    const double v = HALO ? table_point_halo(p, a, b, i)
+                          : table_point(p, p.U + a * int64_t(p.n) * p.before + b, i);
     store_point(p, p.Y + (a * int64_t(p.n_out) + i) * p.before + b, v);
   }
 }
@@ -112,7 +136,7 @@ __device__ __forceinline__ double2 vscale(double al, double2 v) {
 
 // Thread = one vector column (V doubles along b) of one slab a, rows [c0, c1) of the canonical
 // range.  grid.x = column chunks, grid.y = i-chunks, grid.z = a (folded).
-template <int W, int V>
+template <int W, int V, bool HALO>
 __global__ void __launch_bounds__(128) stencil_strided_kernel(const StencilParams p,
                                                                const UniWeights uw, int ichunk,
                                                                int64_t ncolv) {
@@ -135,6 +159,7 @@ __global__ void __launch_bounds__(128) stencil_strided_kernel(const StencilParam
   for (int s = 0; s < W; ++s) w[s] = uw.w[s];
 
   auto row = [&](int j) -> T {
+    if (HALO) return reinterpret_cast<const T*>(halo_row(p, a, j))[colv];
     if (p.periodic) { if (j < 0) j += n; else if (j >= n) j -= n; }
     return u[int64_t(j) * stride];
   };
@@ -318,13 +343,16 @@ int launch_table(const StencilParams& p, int skip_lo, int skip_hi, cudaStream_t 
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = int64_t(pt::sm_count()) * 32;
   if (blocks > cap) blocks = cap;
-  stencil_table_kernel<<<unsigned(blocks), 256, 0, st>>>(p, skip_lo, skip_hi);
+  if (p.Ulo || p.Uhi) stencil_table_kernel<true><<<unsigned(blocks), 256, 0, st>>>(p, skip_lo, skip_hi);
+  else stencil_table_kernel<false><<<unsigned(blocks), 256, 0, st>>>(p, skip_lo, skip_hi);
   return pt::check_launch("pt_stencil_apply(table)");
 }
 
 template <int W>
 int launch_strided(const StencilParams& p, const UniWeights& uw, cudaStream_t st) {
-  const bool vec = (p.before % 2 == 0) && aligned16(p.U) && aligned16(p.Y);
+  const bool halo = p.Ulo || p.Uhi;
+  const bool vec = (p.before % 2 == 0) && aligned16(p.U) && aligned16(p.Y) &&
+                   (!halo || (aligned16(p.Ulo) && aligned16(p.Uhi) && !((p.lo_stride | p.hi_stride) & 1)));
   const int V = vec ? 2 : 1;
   const int64_t ncolv = p.before / V;
   const int64_t gx = (ncolv + 127) / 128;
@@ -342,12 +370,17 @@ int launch_strided(const StencilParams& p, const UniWeights& uw, cudaStream_t st
   for (int64_t a0 = 0; a0 < p.after; a0 += 65535) {
     StencilParams q = p;
     const int64_t na = (p.after - a0 < 65535) ? p.after - a0 : 65535;
-    q.U = p.U + a0 * int64_t(p.n) * p.before;
+    q.U = p.U + a0 * int64_t(p.n - p.halo_lo - p.halo_hi) * p.before;
     q.Y = p.Y + a0 * int64_t(p.n_out) * p.before;
+    if (p.Ulo) q.Ulo = p.Ulo + a0 * p.lo_stride;
+    if (p.Uhi) q.Uhi = p.Uhi + a0 * p.hi_stride;
     q.after = na;
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)na);
-    if (vec) stencil_strided_kernel<W, 2><<<grid, 128, 0, st>>>(q, uw, ichunk, ncolv);
-    else stencil_strided_kernel<W, 1><<<grid, 128, 0, st>>>(q, uw, ichunk, ncolv);
+    if (halo) {
+      if (vec) stencil_strided_kernel<W, 2, true><<<grid, 128, 0, st>>>(q, uw, ichunk, ncolv);
+      else stencil_strided_kernel<W, 1, true><<<grid, 128, 0, st>>>(q, uw, ichunk, ncolv);
+    } else if (vec) stencil_strided_kernel<W, 2, false><<<grid, 128, 0, st>>>(q, uw, ichunk, ncolv);
+    else stencil_strided_kernel<W, 1, false><<<grid, 128, 0, st>>>(q, uw, ichunk, ncolv);
     int rc = pt::check_launch("pt_stencil_apply(strided)");
     if (rc) return rc;
   }
@@ -382,10 +415,17 @@ int launch_fast(const StencilParams& p, const UniWeights& uw, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" int pt_stencil_apply_ex(const double* W, const int32_t* start, int wmax, int n_in, int n_out,
-                                   int shift, const double* U, double* Y, int64_t after, int64_t before,
-                                   int periodic, const pt_uniform_rows* uni, double alpha, double beta,
-                                   pt_stream_t stream) {
+namespace {
+struct HaloArgs {
+  const double* Ulo; const double* Uhi;
+  int halo_lo, halo_hi;
+  int64_t lo_stride, hi_stride;
+};
+
+int stencil_apply_impl(const double* W, const int32_t* start, int wmax, int n_in, int n_out, int shift,
+                       const double* U, double* Y, int64_t after, int64_t before, int periodic,
+                       const pt_uniform_rows* uni, double alpha, double beta, const HaloArgs& h,
+                       pt_stream_t stream) {
   PT_REQUIRE(W && start && U && Y, "pt_stencil_apply: null pointer");
   PT_REQUIRE(wmax >= 1 && wmax <= MAXW, "pt_stencil_apply: wmax=%d outside [1,%d]", wmax, MAXW);
   PT_REQUIRE(n_in >= 1 && n_in >= wmax, "pt_stencil_apply: n=%d smaller than the stencil width %d", n_in, wmax);
@@ -400,6 +440,8 @@ extern "C" int pt_stencil_apply_ex(const double* W, const int32_t* start, int wm
   p.periodic = periodic ? 1 : 0;
   p.alpha = alpha; p.beta = beta;
   p.lo = 0; p.hi = 0;
+  p.Ulo = h.Ulo; p.Uhi = h.Uhi; p.halo_lo = h.halo_lo; p.halo_hi = h.halo_hi;
+  p.lo_stride = h.lo_stride; p.hi_stride = h.hi_stride;
   cudaStream_t st = pt::as_stream(stream);
 
   // canonical rows must read inside the input slab: i + shift - hw >= 0 and i + shift + hw < n_in
@@ -430,6 +472,32 @@ extern "C" int pt_stencil_apply_ex(const double* W, const int32_t* start, int wm
     case 7: return launch_fast<7>(p, uw, st);
     default: return launch_fast<9>(p, uw, st);
   }
+}
+}  // namespace
+
+extern "C" int pt_stencil_apply_ex(const double* W, const int32_t* start, int wmax, int n_in, int n_out,
+                                   int shift, const double* U, double* Y, int64_t after, int64_t before,
+                                   int periodic, const pt_uniform_rows* uni, double alpha, double beta,
+                                   pt_stream_t stream) {
+  const HaloArgs none{nullptr, nullptr, 0, 0, 0, 0};
+  return stencil_apply_impl(W, start, wmax, n_in, n_out, shift, U, Y, after, before, periodic, uni,
+                            alpha, beta, none, stream);
+}
+
+extern "C" int pt_stencil_apply_halo(const double* W, const int32_t* start, int wmax, int n_own,
+                                     int halo_lo, int halo_hi, const double* U, const double* U_lo,
+                                     int64_t lo_stride, const double* U_hi, int64_t hi_stride, double* Y,
+                                     int64_t after, int64_t before, const pt_uniform_rows* uni,
+                                     double alpha, double beta, pt_stream_t stream) {
+  PT_REQUIRE(n_own >= 1 && halo_lo >= 0 && halo_hi >= 0, "pt_stencil_apply_halo: bad slab shape");
+  PT_REQUIRE((halo_lo == 0 || U_lo) && (halo_hi == 0 || U_hi), "pt_stencil_apply_halo: halo buffer is null");
+  PT_REQUIRE(before > 1, "pt_stencil_apply_halo: the sharded axis cannot be the contiguous one");
+  if (halo_lo == 0 && halo_hi == 0)
+    return pt_stencil_apply_ex(W, start, wmax, n_own, n_own, 0, U, Y, after, before, 0, uni, alpha, beta, stream);
+  // an absent side still needs a non-null pointer to select the halo kernels; it is never read
+  const HaloArgs h{halo_lo ? U_lo : U, halo_hi ? U_hi : U, halo_lo, halo_hi, lo_stride, hi_stride};
+  return stencil_apply_impl(W, start, wmax, halo_lo + n_own + halo_hi, n_own, halo_lo, U, Y, after, before,
+                            0, uni, alpha, beta, h, stream);
 }
 
 extern "C" int pt_stencil_apply(const double* W, const int32_t* start, int wmax, int n,
@@ -632,6 +700,7 @@ extern "C" int pt_stencil_grad3(const double* U, double* GX, double* GY, double*
       q.after = P / (q.before * dims[k]);
       q.periodic = 0; q.alpha = 1.0; q.beta = 0.0;
       q.lo = uni[k]->lo; q.hi = uni[k]->hi;
+      q.Ulo = nullptr; q.Uhi = nullptr; q.halo_lo = 0; q.halo_hi = 0; q.lo_stride = 0; q.hi_stride = 0;
       rc = launch_table(q, q.lo, q.hi, st);
       if (rc) return rc;
     }

@@ -13,6 +13,13 @@
                            in place, a "transpose" only redistributes; no local axis permutation that
                            moves the fastest axis is ever needed.
 * ``pencil_apply_sum``   — sum of one operator per axis (e.g. a 3-D Chebyshev Laplacian) on pencils.
+* ``SlabStencil.apply_peer`` / ``PencilPeer`` — the same two paths over **peer memory**
+                           (``pytristan_b200.peer``): the slab stencil loads its halo rows straight
+                           from the neighbours' fields (no exchange, no extended buffer), and the
+                           pencil redistributions are the store phase of the kernels that produce
+                           the data (``pt_dense_apply_scatter`` epilogue + ``pt_peer_scatter`` on a
+                           second stream), separated by device-side flag barriers.  No collective
+                           call on the data path.
 
 The two module-level functions ``_permute3d`` and ``_stencil_local`` are the only places that touch
 the GPU library; the world-size-2 gloo tests replace them with CPU doubles to exercise the
@@ -24,7 +31,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["shard_range", "SlabStencil", "PencilTranspose", "pencil_apply_sum"]
+__all__ = ["shard_range", "SlabStencil", "PencilTranspose", "pencil_apply_sum", "PencilPeer"]
 
 
 def shard_range(total, rank, world):
@@ -192,6 +199,47 @@ class SlabStencil:
         return out
 
 
+    # -- peer-memory form: no exchange, the kernel reads the neighbours' rows over NVLink ---------
+    def peer_field(self, fabric, nfields, plane):
+        """Symmetric field buffer ``(nfields, nloc, plane)`` for ``apply_peer`` (collective)."""
+        rows = [shard_range(self.n, r, self.world)[1] - shard_range(self.n, r, self.world)[0]
+                for r in range(self.world)]
+        buf = fabric.alloc(nfields * max(rows) * plane)
+        buf.rows = rows
+        return buf
+
+    def apply_peer(self, buf, nfields, plane, out, alpha=1.0, beta=0.0):
+        """Differentiate this rank's rows of the field held in ``buf`` (``peer_field``) into
+        ``out`` ``(nfields, nloc, plane)``.  The neighbours' fields must be current: separate the
+        writes of a field from this call by ``fabric.barrier()``."""
+        lib = _lib.load()
+        band = self.band
+        if "uni" not in band:
+            band["uni"] = _lib.uniform_rows(band, self.nloc)
+        uni = band["uni"]
+        lo_peer, hi_peer = self.rank - 1, self.rank + 1
+        if self.periodic:
+            lo_peer %= self.world
+            hi_peer %= self.world
+        u_lo = u_hi = None
+        lo_stride = hi_stride = 0
+        if self.halo_lo:
+            lo_stride = buf.rows[lo_peer] * plane
+            u_lo = ctypes.c_void_p(buf.ptrs[lo_peer] + 8 * (buf.rows[lo_peer] - self.halo_lo) * plane)
+        if self.halo_hi:
+            hi_stride = buf.rows[hi_peer] * plane
+            u_hi = ctypes.c_void_p(buf.ptrs[hi_peer])
+        _lib.check(
+            lib.pt_stencil_apply_halo(_lib.dptr(band["d_w"]), _lib.dptr(band["d_start"]), band["wmax"], self.nloc,
+                                      self.halo_lo, self.halo_hi, ctypes.c_void_p(buf.ptrs[self.rank]), u_lo,
+                                      lo_stride, u_hi, hi_stride, _lib.dptr(out), nfields, plane,
+                                      ctypes.byref(uni) if uni is not None else None, float(alpha), float(beta),
+                                      _lib.stream_ptr()),
+            "pt_stencil_apply_halo",
+        )
+        return out
+
+
 # ---- pencil decomposition -----------------------------------------------------------------------------
 class PencilTranspose:
     """Redistributions of a 3-D field ``(nz, ny, nx)`` (x fastest) over a ``py x pz`` process grid.
@@ -298,3 +346,78 @@ def pencil_apply_sum(ops, u, pencils, back=False):
     if back:
         res = pt.y_to_x(pt.z_to_y(res.contiguous()))
     return res
+
+
+class PencilPeer(PencilTranspose):
+    """Pencil decomposition whose redistributions run over peer memory (``pytristan_b200.peer``).
+
+    Four symmetric buffers of the local block size hold the field and the running sum in layouts
+    B and C.  ``apply_sum`` is then, per rank and with no collective call:
+
+        side stream : u            --pt_peer_scatter-->          peers' uB      (overlaps the Dx kernel)
+        main stream : Dx u         --scatter epilogue-->         peers' accB
+        barrier
+        side stream : uB           --pt_peer_scatter-->          peers' uC      (overlaps the Dy kernel)
+        main stream : Dy uB + accB --scatter epilogue-->         peers' accC
+        barrier
+        main stream : accC += Dz uC                                              (local)
+    """
+
+    def __init__(self, shape, py, pz, fabric, batch=1):
+        torch = _lib.require_cuda()
+        super().__init__(shape, py, pz, rank=fabric.rank, world=fabric.world, groups=(None, None))
+        self.fabric, self.batch = fabric, int(batch)
+        self.count = self.batch * self.nzl * self.nyl * self.nx
+        self.uB, self.accB, self.uC, self.accC = (fabric.alloc(self.count) for _ in range(4))
+        row = [self.rz * self.py + y for y in range(self.py)]
+        col = [z * self.py + self.ry for z in range(self.pz)]
+        self.row_ranks, self.col_ranks = row, col
+        self._side = torch.cuda.Stream()
+        self.maps = {}
+        for name, bufB, bufC in (("u", self.uB, self.uC), ("acc", self.accB, self.accC)):
+            self.maps[name + "_AB"] = fabric.scatter_map(bufB, row, *self.map_ab())
+            self.maps[name + "_BC"] = fabric.scatter_map(bufC, col, *self.map_bc())
+
+    # destination maps as (chunk, a_inner, s_outer, s_inner, s_i, offset); see pt_scatter_map
+    def map_ab(self):
+        """Layout A ``(lead*nyl, nx)`` -> layout B ``(lead, ny, nxl)`` of the rank owning x // nxl."""
+        return (self.nxl, self.nyl, self.ny * self.nxl, self.nxl, 1, self.ry * self.nyl * self.nxl)
+
+    def map_bc(self):
+        """Layout B ``(batch*nzl, ny, nxl)`` -> layout C ``(batch, nz, nyl2, nxl)`` of the rank owning y // nyl2."""
+        blk = self.nyl2 * self.nxl
+        return (self.nyl2, self.nzl, self.nz * blk, blk, self.nxl, self.rz * self.nzl * blk)
+
+    def apply_sum(self, ops, u):
+        """``sum_k ops[k] along axis k`` of the field whose layout-A block is ``u``
+        ``(batch, nzl, nyl, nx)``; returns the layout-C block ``(batch, nz, nyl2, nxl)`` (a view
+        of the symmetric buffer ``accC``, valid until the next call)."""
+        torch = _lib.torch_mod()
+        lib = _lib.load()
+        dx, dy, dz = ops
+        fab = self.fabric
+        main = torch.cuda.current_stream()
+        side = self._side
+        lead = self.batch * self.nzl
+        u = u.reshape(-1)
+        # ---- A -> B
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _lib.check(lib.pt_peer_scatter(_lib.dptr(u), self.nx, lead * self.nyl, 1,
+                                           ctypes.byref(self.maps["u_AB"]), _lib.stream_ptr()), "pt_peer_scatter")
+        dx._apply_scatter(u, lead * self.nyl, self.nx, 1, None, 1.0, 0.0, self.maps["acc_AB"])
+        main.wait_stream(side)
+        fab.barrier()
+        # ---- B -> C
+        uB, accB = self.uB.local, self.accB.local
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _lib.check(lib.pt_peer_scatter(_lib.dptr(uB), self.ny, lead, self.nxl,
+                                           ctypes.byref(self.maps["u_BC"]), _lib.stream_ptr()), "pt_peer_scatter")
+        dy._apply_scatter(uB, lead, self.ny, self.nxl, accB, 1.0, 1.0, self.maps["acc_BC"])
+        main.wait_stream(side)
+        fab.barrier()
+        # ---- C: local
+        dz._apply_device(self.uC.local, self.batch, self.nz, self.nyl2 * self.nxl, self.accC.local, 1.0, 1.0,
+                         None, None)
+        return self.accC.local.view(self.batch, self.nz, self.nyl2, self.nxl)

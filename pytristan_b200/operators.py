@@ -235,6 +235,17 @@ class _DiffMat(np.ndarray):
         )
         return d_y
 
+    def _apply_scatter(self, d_u, after, n, before, c, alpha, beta, smap):
+        """``alpha * D u + beta * c`` stored through the pencil-redistribution map ``smap``
+        (``pt_dense_apply_scatter``: the epilogue writes into the peers' buffers)."""
+        lib = _lib.load()
+        _lib.check(
+            lib.pt_dense_apply_scatter(_lib.dptr(self._packed_device()), n, n, _lib.dptr(d_u), _lib.dptr(c),
+                                       after, before, float(alpha), float(beta), ctypes.byref(smap),
+                                       _lib.stream_ptr()),
+            "pt_dense_apply_scatter",
+        )
+
     def matmul(self, other):
         """``D @ other``: ``other`` with leading dimension ``n`` is multiplied as a matrix
         (``D @ M``); a flat field (or stack of fields) on the bound grid is differentiated along
