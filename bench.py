@@ -416,6 +416,15 @@ def run_gpu_sharded(args, spec):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = spec["n"]
     gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
+    peer = args.comm == "peer"
+    fab = None
+    if peer:
+        from pytristan_b200.peer import PeerFabric
+
+        if not dist.is_initialized():
+            os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", RANK="0", WORLD_SIZE="1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        fab = PeerFabric()
     if spec["kind"] == "slab":
         x = np.linspace(0.0, 1.0, n)
         F = pt.FinDiffMat(x, order=1, accuracy=6)
@@ -423,32 +432,56 @@ def run_gpu_sharded(args, spec):
         fx, fy = pt.FinDiffMat(x, order=1, accuracy=6), pt.FinDiffMat(x, order=1, accuracy=6)
         fx.npts, fx.axis = (n, n, plan.nloc), 0
         fy.npts, fy.axis = (n, n, plan.nloc), 1
-        ext = torch.zeros(plan.ext_shape(1, n * n), dtype=torch.float64, device="cuda")
-        plan.interior(ext).copy_(torch.randn(1, plan.nloc, n * n, dtype=torch.float64, device="cuda", generator=gen))
-        own = plan.interior(ext)                       # contiguous: slabs of the slowest axis
         outs = [torch.empty(plan.nloc * n * n, dtype=torch.float64, device="cuda") for _ in range(3)]
+        field = torch.randn(1, plan.nloc, n * n, dtype=torch.float64, device="cuda", generator=gen)
+        if peer:
+            buf = plan.peer_field(fab, 1, n * n)       # the field lives in peer-mapped memory
+            own = buf.local[:plan.nloc * n * n]
+            own.view(1, plan.nloc, n * n).copy_(field)
 
-        def step():
-            plan.exchange(ext)                          # halo planes over NVLink (NCCL send/recv)
-            fx.apply(own.reshape(-1), out=outs[0])
-            fy.apply(own.reshape(-1), out=outs[1])
-            plan.apply(ext, out=outs[2].view(1, plan.nloc, n * n))
+            def step():
+                fab.barrier()                           # neighbours' fields are current (device flag barrier)
+                fx.apply(own, out=outs[0])
+                fy.apply(own, out=outs[1])
+                plan.apply_peer(buf, 1, n * n, outs[2].view(1, plan.nloc, n * n))   # halo rows loaded over NVLink
 
-        launches = 5
+            launches = 6                                # barrier + 3 stencil kernels + 2 boundary-row kernels
+        else:
+            ext = torch.zeros(plan.ext_shape(1, n * n), dtype=torch.float64, device="cuda")
+            plan.interior(ext).copy_(field)
+            own = plan.interior(ext)                       # contiguous: slabs of the slowest axis
+
+            def step():
+                plan.exchange(ext)                          # halo planes over NVLink (NCCL send/recv)
+                fx.apply(own.reshape(-1), out=outs[0])
+                fy.apply(own.reshape(-1), out=outs[1])
+                plan.apply(ext, out=outs[2].view(1, plan.nloc, n * n))
+
+            launches = 5
+        del field
         local_alg = 3 * 16.0 * plan.nloc * n * n
         host_bytes = plan.nloc * n * n * 8
     else:
         py = 2 if world % 2 == 0 else 1
         pz = world // py
-        pen = ptd.PencilTranspose((n, n, n), py, pz, rank, world)
         xs = pt.cheb(n)
         ops = [pt.ChebMat(xs, order=2) for _ in range(3)]
-        u = torch.randn(pen.nzl, pen.nyl, n, dtype=torch.float64, device="cuda", generator=gen)
+        if peer:
+            pen = ptd.PencilPeer((n, n, n), py, pz, fab)
+            u = torch.randn(pen.nzl, pen.nyl, n, dtype=torch.float64, device="cuda", generator=gen)
 
-        def step():
-            return ptd.pencil_apply_sum(ops, u, pen, back=False)
+            def step():
+                return pen.apply_sum(ops, u)
 
-        launches = 3 + 2 + 2 + 1          # 3 DMMA kernels, pack/unpack of two redistributions (z unpack only for batch)
+            launches = 3 + 2 + 2              # 3 DMMA kernels (two with scatter epilogue), 2 peer scatters, 2 barriers
+        else:
+            pen = ptd.PencilTranspose((n, n, n), py, pz, rank, world)
+            u = torch.randn(pen.nzl, pen.nyl, n, dtype=torch.float64, device="cuda", generator=gen)
+
+            def step():
+                return ptd.pencil_apply_sum(ops, u, pen, back=False)
+
+            launches = 3 + 2 + 2 + 1          # 3 DMMA kernels, pack/unpack of two redistributions (z unpack only for batch)
         local_alg = 3 * 2.0 * n * (n ** 3) / world
         host_bytes = u.numel() * 8
 
@@ -495,11 +528,16 @@ def run_gpu_sharded(args, spec):
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": spec["name"], "npts": list(spec["npts"]), "ops": [o[0] for o in spec["ops"]],
-                           "sharding": "z slabs + halo exchange" if spec["kind"] == "slab" else "2-D pencils, all_to_all redistributions",
+                           "sharding": ("z slabs, " + ("halo rows loaded from the neighbours' memory (peer loads, device flag barrier)" if peer else "halo exchange (NCCL send/recv)")) if spec["kind"] == "slab"
+                           else ("2-D pencils, " + ("redistribution fused into the DMMA epilogue / peer-store scatter over NVLink, device flag barriers" if peer else "pack + all_to_all + unpack")),
+                           "comm": args.comm,
                            "l2": "per-rank field larger than L2" if host_bytes > 126e6 else "per-rank field fits L2 (strong scaling)"},
                 "roofline": roof, "cpu_baseline": None,
                 "e2e": None, "gpu_launches": args.steps * launches * world, "clocks": sampler.summary()}
         print(json.dumps(line))
+    if fab is not None:
+        fab.check()
+        fab.close()
     if dist.is_initialized():
         dist.destroy_process_group()
 
@@ -512,6 +550,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="channel_1024x257_b64")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
+                    help="sharded workloads: peer-memory kernels (default) or the NCCL exchange/all_to_all path")
     args = ap.parse_args()
     spec = workload_spec(args.workload)
     if args.impl == "reference":
