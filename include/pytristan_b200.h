@@ -58,6 +58,18 @@ int pt_gen_linspace(double* x, double start, double stop, int64_t n, pt_stream_t
 /* Chebyshev-Gauss-Lobatto nodes x_j = cos(fl(fl(j*pi)/(n-1))), descending (grid.py:75);
  * if mapped != 0 additionally fl(fl(fl(fl(1-x)/2)*fl(xmax-xmin))+xmin) (grid.py:77). */
 int pt_gen_cheb(double* x, int64_t n, int mapped, double xmin, double xmax, pt_stream_t stream);
+/* The same nodes with the HOST libm's cosine reproduced bit for bit on the device, so that device
+ * generated nodes equal numpy.cos-generated ones (grid.py:75) at every node, not just within an
+ * ulp: glibc's dbl-64 cos is not correctly rounded, and its x86-64 FMA and baseline builds differ
+ * from each other.  libm selects the build the host runs (the Python side probes numpy.cos). */
+enum pt_libm_model {
+  PT_LIBM_GLIBC_FMA = 1,   /* glibc >= 2.28 dbl-64 s_sin.c, -mfma -mavx2 build (__cos_fma) */
+  PT_LIBM_GLIBC_NOFMA = 2  /* same source, baseline build (__cos_sse2 / __cos_avx)          */
+};
+int pt_gen_cheb_libm(double* x, int64_t n, int mapped, double xmin, double xmax, int libm,
+                     pt_stream_t stream);
+/* y[i] = cos(t[i]) with that cosine (|t| < 105414350; beyond that the CUDA cosine). */
+int pt_cos_libm(const double* t, double* y, int64_t n, int libm, pt_stream_t stream);
 /* In-place affine map of reference nodes, the arithmetic of grid.py:77 bit for bit. */
 int pt_cheb_map(double* x, int64_t n, double xmin, double xmax, pt_stream_t stream);
 /* Expand ndim 1-D axis arrays into the reference Grid layout (grid.py:83-88): out is

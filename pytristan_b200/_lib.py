@@ -63,6 +63,8 @@ SIGNATURES = {
     "pt_gen_linspace": (_c_i32, [_c_ptr, _c_f64, _c_f64, _c_i64, _c_ptr]),
     "pt_gen_cheb": (_c_i32, [_c_ptr, _c_i64, _c_i32, _c_f64, _c_f64, _c_ptr]),
     "pt_cheb_map": (_c_i32, [_c_ptr, _c_i64, _c_f64, _c_f64, _c_ptr]),
+    "pt_gen_cheb_libm": (_c_i32, [_c_ptr, _c_i64, _c_i32, _c_f64, _c_f64, _c_i32, _c_ptr]),
+    "pt_cos_libm": (_c_i32, [_c_ptr, _c_ptr, _c_i64, _c_i32, _c_ptr]),
     "pt_grid_expand": (_c_i32, [_c_ptr, ctypes.POINTER(_c_i64), _c_i32, _c_i32, _c_ptr, _c_ptr]),
     "pt_grid_axpoints": (_c_i32, [_c_ptr, _c_i64, _c_i64, _c_ptr, _c_ptr]),
     "pt_gen_chebmat": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr]),
@@ -101,6 +103,34 @@ SIGNATURES = {
 }
 
 SCALE_NONE, SCALE_ROW, SCALE_AFTER, SCALE_BEFORE = 0, 1, 2, 3
+LIBM_GLIBC_FMA, LIBM_GLIBC_NOFMA = 1, 2
+
+# arguments on which the two x86-64 builds of glibc's cos disagree: (x, cos_fma(x), cos_nofma(x)) bits
+_LIBM_PROBES = (
+    (0x4006994ac2a0c6a4, 0xbfee687cff59a44f, 0xbfee687cff59a450),
+    (0x3ffc4fd49259333f, 0xbfc94408859fa3c5, 0xbfc94408859fa3c4),
+    (0x40001a0458d397a5, 0xbfdb5eda16e37d6d, 0xbfdb5eda16e37d6e),
+    (0x3fe49acc91af868a, 0x3fe997a81c219b77, 0x3fe997a81c219b76),
+    (0x3fe877bd71546efa, 0x3fe717bd07934ca8, 0x3fe717bd07934ca7),
+    (0x3ffdb39d631e5038, 0xbfd20735577cc5de, 0xbfd20735577cc5df),
+)
+_libm_model = None
+
+
+def host_libm_model():
+    """Which build of glibc's cos ``numpy.cos`` runs on this host (pt_libm_model), or 0 when it
+    is neither: decided by evaluating numpy.cos on arguments where the builds differ."""
+    global _libm_model
+    if _libm_model is None:
+        x = np.array([p[0] for p in _LIBM_PROBES], dtype=np.uint64).view(np.float64)
+        got = np.cos(x).view(np.uint64)
+        if all(int(g) == p[1] for g, p in zip(got, _LIBM_PROBES)):
+            _libm_model = LIBM_GLIBC_FMA
+        elif all(int(g) == p[2] for g, p in zip(got, _LIBM_PROBES)):
+            _libm_model = LIBM_GLIBC_NOFMA
+        else:
+            _libm_model = 0
+    return _libm_model
 
 _lib = None
 

@@ -6,6 +6,7 @@
 // (hard part 2).  The operator generators use the same operation order as
 // oracle/operators.py for the same reason.
 #include "common.cuh"
+#include "glibc_cos.cuh"
 
 namespace {
 
@@ -43,6 +44,23 @@ __global__ void cheb_kernel(double* __restrict__ x, int64_t n, int mapped, doubl
   double v = cos(theta);
   if (mapped) v = affine_map(v, xmin, xmax);
   x[j] = v;
+}
+
+// the same nodes with the host libm's cosine reproduced bit for bit (glibc_cos.cuh)
+template <bool FMA>
+__global__ void cheb_libm_kernel(double* __restrict__ x, int64_t n, int mapped, double xmin, double xmax) {
+  const int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (j >= n) return;
+  const double theta = __ddiv_rn(__dmul_rn(double(j), kPi), double(n - 1));
+  double v = ptglibc::glibc_cos<FMA>(theta);
+  if (mapped) v = affine_map(v, xmin, xmax);
+  x[j] = v;
+}
+
+template <bool FMA>
+__global__ void cos_libm_kernel(const double* __restrict__ t, double* __restrict__ y, int64_t n) {
+  const int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (j < n) y[j] = ptglibc::glibc_cos<FMA>(t[j]);
 }
 
 __global__ void cheb_map_kernel(double* __restrict__ x, int64_t n, double xmin, double xmax) {
@@ -416,6 +434,29 @@ extern "C" int pt_gen_cheb(double* x, int64_t n, int mapped, double xmin, double
   PT_REQUIRE(x, "pt_gen_cheb: null pointer");
   cheb_kernel<<<blocks_for(n, 256), 256, 0, pt::as_stream(stream)>>>(x, n, mapped, xmin, xmax);
   return pt::check_launch("pt_gen_cheb");
+}
+
+extern "C" int pt_gen_cheb_libm(double* x, int64_t n, int mapped, double xmin, double xmax, int libm,
+                                pt_stream_t stream) {
+  PT_REQUIRE(n >= 0, "pt_gen_cheb_libm: n must be non-negative");
+  PT_REQUIRE(libm == PT_LIBM_GLIBC_FMA || libm == PT_LIBM_GLIBC_NOFMA, "pt_gen_cheb_libm: unknown libm model %d", libm);
+  if (n == 0) return PT_OK;
+  PT_REQUIRE(x, "pt_gen_cheb_libm: null pointer");
+  if (libm == PT_LIBM_GLIBC_FMA)
+    cheb_libm_kernel<true><<<blocks_for(n, 256), 256, 0, pt::as_stream(stream)>>>(x, n, mapped, xmin, xmax);
+  else
+    cheb_libm_kernel<false><<<blocks_for(n, 256), 256, 0, pt::as_stream(stream)>>>(x, n, mapped, xmin, xmax);
+  return pt::check_launch("pt_gen_cheb_libm");
+}
+
+extern "C" int pt_cos_libm(const double* t, double* y, int64_t n, int libm, pt_stream_t stream) {
+  PT_REQUIRE(n >= 0, "pt_cos_libm: n must be non-negative");
+  PT_REQUIRE(libm == PT_LIBM_GLIBC_FMA || libm == PT_LIBM_GLIBC_NOFMA, "pt_cos_libm: unknown libm model %d", libm);
+  if (n == 0) return PT_OK;
+  PT_REQUIRE(t && y, "pt_cos_libm: null pointer");
+  if (libm == PT_LIBM_GLIBC_FMA) cos_libm_kernel<true><<<blocks_for(n, 256), 256, 0, pt::as_stream(stream)>>>(t, y, n);
+  else cos_libm_kernel<false><<<blocks_for(n, 256), 256, 0, pt::as_stream(stream)>>>(t, y, n);
+  return pt::check_launch("pt_cos_libm");
 }
 
 extern "C" int pt_cheb_map(double* x, int64_t n, double xmin, double xmax, pt_stream_t stream) {

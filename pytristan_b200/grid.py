@@ -25,6 +25,7 @@ from ._manager import ObjectManager
 
 __all__ = [
     "cheb",
+    "cheb_device",
     "Grid",
     "DeviceGrid",
     "_get_grid_manager",
@@ -58,6 +59,32 @@ def cheb(npts, xmin=None, xmax=None):
     if xmin is None and xmax is None:
         return nodes
     return (1.0 - nodes) / 2.0 * (xmax - xmin) + xmin
+
+
+def cheb_device(npts, xmin=None, xmax=None):
+    """``cheb`` evaluated on the GPU: a CUDA float64 tensor holding the same nodes **bit for bit**.
+
+    The device kernel (``pt_gen_cheb_libm``) reproduces the cosine of the host's libm, which is
+    what ``numpy.cos`` — and therefore the reference (grid.py:75) — evaluates; glibc's cosine is not
+    correctly rounded, so an accurate device cosine differs from it at a few nodes for N >= 512.
+    When the host libm is not one of the two glibc builds the kernel models, the nodes are
+    computed by ``cheb`` and uploaded (still bit-identical; only O(N) values)."""
+    try:
+        n = operator.index(npts)
+    except TypeError as exc:
+        raise TypeError("npts must be an integer.") from exc
+    if n < 0:
+        raise ValueError(f"Number of grid points, {n}, must be a positive integer.")
+    torch = _lib.require_cuda()
+    model = _lib.host_libm_model()
+    mapped = not (xmin is None and xmax is None)
+    if model == 0 or n < 2:
+        return torch.from_numpy(np.ascontiguousarray(cheb(n, xmin, xmax), dtype=np.float64)).cuda()
+    lo, hi = (float(xmin), float(xmax)) if mapped else (0.0, 0.0)   # one bound None -> TypeError like the reference
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().pt_gen_cheb_libm(_lib.dptr(x), n, int(mapped), lo, hi, model, _lib.stream_ptr()),
+               "pt_gen_cheb_libm")
+    return x
 
 
 def _expand_axes(axes, dtype):
