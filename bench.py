@@ -48,6 +48,14 @@ def workload_spec(name):
                     ops=[("d/dx FourMat n=1024 axis0 (K2)", "four", 0, 1, 2.0 * NX * P * BATCH),
                          ("d2/dy2 ChebMat n=257 axis1 (K1)", "cheb", 1, 2, 2.0 * NY * P * BATCH)],
                     points_per_step=2 * P * BATCH)
+    if name == "channel_1024x257_b64_fft":
+        # same operators and fields as the default workload; d/dx evaluated by FourMat(method="fft")
+        # (pt_fourier_apply: the same linear map in O(n log n), HBM-bound) — SURVEY.md 8f rank 2
+        P = NX * NY
+        return dict(name=name, npts=(NX, NY), batch=BATCH, bound="tensor",
+                    ops=[("d/dx FourMat n=1024 axis0 (FFT)", "four_fft", 0, 1, 16.0 * P * BATCH),
+                         ("d2/dy2 ChebMat n=257 axis1 (K1)", "cheb", 1, 2, 2.0 * NY * P * BATCH)],
+                    points_per_step=2 * P * BATCH)
     if name == "fd6_512cube":
         P = 512 ** 3
         return dict(name=name, npts=(512, 512, 512), batch=1, bound="hbm",
@@ -81,7 +89,7 @@ def workload_spec(name):
 def axis_nodes(spec):
     import pytristan_b200 as pt
 
-    if spec["name"] == "channel_1024x257_b64":
+    if spec["name"].startswith("channel_1024x257_b64"):
         return [np.linspace(0.0, 2 * np.pi - 2 * np.pi / NX, NX), pt.cheb(NY, -1.0, 1.0)]
     if spec["name"] == "cheb2048_b8192":
         return [np.linspace(0.0, 1.0, 8192), pt.cheb(2048, -1.0, 1.0)]
@@ -151,7 +159,7 @@ def cpu_operators(spec, nodes):
     mats = []
     for (_, kind, axis, order, _) in spec["ops"]:
         x = nodes[axis]
-        if kind == "four":
+        if kind in ("four", "four_fft"):
             n = x.size
             mats.append(("dense", oracle.four_mat(n, n * ((x[-1] - x[0]) / (n - 1)), order)))
         elif kind == "cheb":
@@ -225,6 +233,8 @@ def build_ops(spec, nodes):
         x = nodes[axis]
         if kind == "four":
             op = pt.FourMat(x, order=order)
+        elif kind == "four_fft":
+            op = pt.FourMat(x, order=order, method="fft")
         elif kind == "cheb":
             op = pt.ChebMat(x, order=order)
         else:
@@ -367,7 +377,7 @@ def run_gpu(args, spec):
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        sample_b = B if spec["name"] == "channel_1024x257_b64" else 1
+        sample_b = B if spec["name"].startswith("channel_1024x257_b64") else 1
         if spec["name"].startswith("fd6_1024"):
             cpu = {"value": None, "unit": "points/s", "cores": cores, "kind": "port",
                    "sample": "skipped: 1024^3 slice-sum oracle needs > 60 s"}

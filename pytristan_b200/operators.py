@@ -355,11 +355,18 @@ class ChebMat(_DiffMat):
 class FourMat(_DiffMat):
     """Fourier spectral differentiation matrix (orders 1-8) on an equispaced periodic axis
     whose endpoint is excluded, e.g. the theta axis of ``get_polar_grid`` (reference
-    grid.py:505).  ``period`` defaults to ``n * spacing``."""
+    grid.py:505).  ``period`` defaults to ``n * spacing``.
+
+    ``method`` selects how ``apply`` evaluates the product: ``"dense"`` (default; the matrix on the
+    FP64 tensor cores, ``pt_dense_apply``) or ``"fft"`` (``pt_fourier_apply``: the same linear map
+    through shared-memory FFTs, O(n log n) and HBM-bound; power-of-two ``n`` up to 4096, otherwise
+    the dense path runs).  The ndarray itself is the dense matrix either way."""
 
     _KIND = "four"
 
-    def __new__(cls, grid, axis=0, order=1, period=None):
+    def __new__(cls, grid, axis=0, order=1, period=None, method="dense"):
+        if method not in ("dense", "fft"):
+            raise ValueError("FourMat: method must be 'dense' or 'fft'")
         nodes, npts, axis, gnum = _resolve_axis(grid, axis)
         order = operator.index(order)
         if not 1 <= order <= 8:
@@ -383,7 +390,34 @@ class FourMat(_DiffMat):
                        "pt_gen_fourmat_general")
         obj = cls._wrap(d_mat, npts, axis, order, gnum)
         obj.period = float(period)
+        obj.method = method
+        obj._tw = None
         return obj
+
+    def __array_finalize__(self, obj):
+        super().__array_finalize__(obj)
+        self.period = getattr(obj, "period", None)
+        self.method = "dense"
+        self._tw = None
+
+    def _apply_device(self, d_u, after, n, before, out, alpha, beta, scale, scale_mode):
+        if getattr(self, "method", "dense") == "fft" and scale is None and self.period is not None:
+            lib = _lib.load()
+            if n >= 4 and n & (n - 1) == 0 and n <= 4096:
+                if self._tw is None:
+                    self._tw = _lib.empty((2 * n,))
+                    _lib.check(lib.pt_fourier_twiddles(n, _lib.dptr(self._tw), _lib.stream_ptr()),
+                               "pt_fourier_twiddles")
+                d_y = self._prepare_out(d_u, out, beta)
+                rc = lib.pt_fourier_apply(_lib.dptr(self._tw), n, float(self.period), int(self.order),
+                                          _lib.dptr(d_u), _lib.dptr(d_y), after, before, float(alpha),
+                                          float(beta), _lib.stream_ptr())
+                if rc == 0:
+                    return d_y
+                if rc != -3:
+                    _lib.check(rc, "pt_fourier_apply")
+                out = d_y      # unsupported layout (odd stride / alignment): dense kernel below
+        return super()._apply_device(d_u, after, n, before, out, alpha, beta, scale, scale_mode)
 
 
 class FinDiffMat(_DiffMat):

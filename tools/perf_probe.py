@@ -56,8 +56,44 @@ def stencil(npts, axis, batch, label, order=1, acc=6):
                       "frac_hbm": round(by / ms * 1e-6 / HBM, 3), "gpts_s": round(P * batch / ms * 1e-6, 2)}))
 
 
+def fourier(npts, axis, batch, label, order=1):
+    n = npts[axis]
+    x = np.arange(n) * (2 * np.pi / n)
+    P = int(np.prod(npts))
+    U = torch.randn(batch, P, dtype=torch.float64, device="cuda")
+    Y = torch.empty_like(U)
+    for method in (("fft",) if "cfg" in sys.argv[1] else ("fft", "dense")):
+        F = pt.FourMat(x, order=order, method=method)
+        F.npts, F.axis = tuple(npts), axis
+        F.apply(U, out=Y)
+        ms = timeit(lambda: F.apply(U, out=Y))
+        by = 16.0 * P * batch
+        print(json.dumps({"case": f"{label} [{method}]", "ms": round(ms, 4), "gbs": round(by / ms * 1e-6, 1),
+                          "frac_hbm": round(by / ms * 1e-6 / HBM, 3), "gpts_s": round(P * batch / ms * 1e-6, 2),
+                          "dense_equiv_tflops": round(2.0 * n * P * batch / ms * 1e-9, 1)}))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "fftcfg":
+        lib = _lib.load()
+        for cfg in (0, 1, 2):
+            lib.pt_debug_set_fft_config(cfg)
+            print("== fft config", cfg)
+            fourier((1024, 257), 0, 64, "cfg2 d/dx FourMat n=1024 axis0")
+            fourier((256, 4096), 0, 16, "n=256 axis0")
+            fourier((4096, 1024), 0, 4, "n=4096 axis0")
+            fourier((64, 1024, 64), 1, 4, "n=1024 axis1 before=64")
+            fourier((512, 512, 64), 1, 1, "n=512 axis1 before=512")
+        sys.exit(0)
+    if what == "fft":
+        fourier((1024, 257), 0, 64, "cfg2 d/dx FourMat n=1024 axis0")
+        fourier((1024, 512), 0, 64, "cfg3 D2_theta n=1024 axis0", order=2)
+        fourier((256, 4096), 0, 16, "n=256 axis0")
+        fourier((4096, 1024), 0, 4, "n=4096 axis0")
+        fourier((64, 1024, 64), 1, 4, "n=1024 axis1 before=64")
+        fourier((512, 512, 64), 1, 1, "n=512 axis1 before=512")
+        sys.exit(0)
     if what == "tma":
         import ctypes
         lib = _lib.load()
