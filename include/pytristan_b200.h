@@ -136,14 +136,16 @@ int pt_dense_apply(const double* packed, int n_out, int n_in, const double* U, d
 /* ---- FourMat through the FFT ----------------------------------------- */
 /* tw[2*m], tw[2*m+1] = cos, -sin of 2 pi m / n for m < n (n complex doubles); n a power of two. */
 int pt_fourier_twiddles(int n, double* tw, pt_stream_t stream);
-/* Y[a,:,b] = alpha * (D U[a,:,b]) + beta * Y[a,:,b] with D the order-`order` Fourier spectral
+/* Y[a,:,b] = alpha * scale[a % scale_len] * (D U[a,:,b]) + beta * Y[a,:,b] (scale may be NULL:
+ * no scaling; it is the PT_SCALE_AFTER epilogue of pt_dense_apply) with D the order-`order` Fourier spectral
  * differentiation matrix on n equispaced periodic nodes of period `period` — the same linear map
  * as the dense matrix of pt_gen_fourmat / pt_gen_fourmat_general, evaluated by shared-memory FFTs
  * (O(n log n), HBM-bound: 16 B/point).  Returns PT_ERR_UNSUPPORTED (and does nothing) unless n is
  * a power of two in [4, 4096] and, on a strided axis (before > 1), before is even and the fields
  * are 16-byte aligned: callers then use pt_dense_apply. */
 int pt_fourier_apply(const double* tw, int n, double period, int order, const double* U, double* Y,
-                     int64_t after, int64_t before, double alpha, double beta, pt_stream_t stream);
+                     int64_t after, int64_t before, double alpha, double beta, const double* scale,
+                     int64_t scale_len, pt_stream_t stream);
 
 /* ---- K3/K4: banded (finite-difference) application --------------------------------------- */
 /* Optional description of the uniform part of a band (all pointers are HOST pointers).  Rows

@@ -81,7 +81,7 @@ SIGNATURES = {
                                 _c_f64, _c_ptr, _c_i32, _c_i64, _c_ptr]),
     "pt_fourier_twiddles": (_c_i32, [_c_i32, _c_ptr, _c_ptr]),
     "pt_fourier_apply": (_c_i32, [_c_ptr, _c_i32, _c_f64, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64, _c_f64,
-                                  _c_ptr]),
+                                  _c_ptr, _c_i64, _c_ptr]),
     "pt_stencil_apply": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64,
                                   _c_i32, ctypes.POINTER(UniformRows), _c_f64, _c_f64, _c_ptr]),
     "pt_stencil_apply_ex": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64,

@@ -32,6 +32,8 @@ struct FftParams {
   int order;
   double s;                         // 2 pi / period
   double alpha_over_n, beta;
+  const double* __restrict__ scale; // optional: result of slab/row a is multiplied by scale[a % scale_len]
+  int64_t scale_len;
 };
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -125,6 +127,9 @@ struct GlobalIO {
   int64_t hb;          // strided: complex columns per row
   int64_t left;        // contiguous: real rows left from base0; strided: complex columns left from cb
   double beta;
+  const double* __restrict__ scale;   // PT_SCALE_AFTER vector or nullptr
+  int64_t scale_len;
+  double slab_scale;   // strided: scale of this group's slab a
 
   __device__ __forceinline__ double2 load(int sq, int i) const {
     if (!STRIDED) {
@@ -140,6 +145,10 @@ struct GlobalIO {
   __device__ __forceinline__ void store(int sq, int i, double2 z) const {
     if (!STRIDED) {
       const int64_t r = 2 * sq;
+      if (scale) {
+        if (r < left) z.x *= scale[(base0 + r) % scale_len];
+        if (r + 1 < left) z.y *= scale[(base0 + r + 1) % scale_len];
+      }
       if (r < left) {
         double* y = Y + (base0 + r) * N + i;
         *y = beta != 0.0 ? fma(beta, *y, z.x) : z.x;
@@ -151,6 +160,7 @@ struct GlobalIO {
       return;
     }
     if (sq >= left) return;
+    if (scale) { z.x *= slab_scale; z.y *= slab_scale; }
     double2* y = reinterpret_cast<double2*>(Y) + base0 + int64_t(i) * hb + sq;
     if (beta != 0.0) { const double2 o = *y; z.x = fma(beta, o.x, z.x); z.y = fma(beta, o.y, z.y); }
     *y = z;
@@ -299,6 +309,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) fourier_fft_kernel(cons
   for (int64_t g = blockIdx.x; g < p.ngroups; g += gridDim.x) {
     GlobalIO<LOG2N, STRIDED> io;
     io.U = p.U; io.Y = p.Y; io.beta = p.beta; io.hb = hb;
+    io.scale = p.scale; io.scale_len = p.scale_len; io.slab_scale = 1.0;
     if (!STRIDED) {
       io.base0 = g * (2 * P::S);
       io.left = p.after - io.base0;
@@ -306,6 +317,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) fourier_fft_kernel(cons
       const int64_t a = g / p.groups_per_a, cb = (g - a * p.groups_per_a) * P::S;
       io.base0 = a * N * hb + cb;
       io.left = hb - cb;
+      if (p.scale) io.slab_scale = p.scale[a % p.scale_len];
     }
     if constexpr (P::NR16 == 0) {
       stage_middle<LOG2N, true, STRIDED, NT, TILE>(data, tw, io, p);
@@ -409,8 +421,10 @@ extern "C" int pt_fourier_twiddles(int n, double* tw, pt_stream_t stream) {
 }
 
 extern "C" int pt_fourier_apply(const double* tw, int n, double period, int order, const double* U, double* Y,
-                                int64_t after, int64_t before, double alpha, double beta, pt_stream_t stream) {
+                                int64_t after, int64_t before, double alpha, double beta,
+                                const double* scale, int64_t scale_len, pt_stream_t stream) {
   PT_REQUIRE(tw && U && Y, "pt_fourier_apply: null pointer");
+  PT_REQUIRE(scale == nullptr || scale_len > 0, "pt_fourier_apply: scale_len must be > 0");
   PT_REQUIRE(order >= 1 && order <= 8, "pt_fourier_apply: order=%d outside [1,8]", order);
   PT_REQUIRE(period > 0.0, "pt_fourier_apply: period must be positive");
   PT_REQUIRE(after >= 0 && before >= 1, "pt_fourier_apply: bad field shape");
@@ -430,6 +444,7 @@ extern "C" int pt_fourier_apply(const double* tw, int n, double period, int orde
   p.after = after; p.before = before;
   p.order = order; p.s = 6.283185307179586476925286766559 / period;
   p.alpha_over_n = alpha / double(n); p.beta = beta;
+  p.scale = scale; p.scale_len = scale ? scale_len : 1;
   cudaStream_t st = pt::as_stream(stream);
   return strided ? dispatch_fft<true>(log2n, p, st) : dispatch_fft<false>(log2n, p, st);
 }

@@ -401,9 +401,14 @@ class FourMat(_DiffMat):
         self._tw = None
 
     def _apply_device(self, d_u, after, n, before, out, alpha, beta, scale, scale_mode):
-        if getattr(self, "method", "dense") == "fft" and scale is None and self.period is not None:
+        if (getattr(self, "method", "dense") == "fft" and (scale is None or scale_mode == "after")
+                and self.period is not None):
             lib = _lib.load()
             if n >= 4 and n & (n - 1) == 0 and n <= 4096:
+                d_scale, slen = None, 0
+                if scale is not None:
+                    d_scale, _ = _field_to_device(scale)
+                    slen = d_scale.numel()
                 if self._tw is None:
                     self._tw = _lib.empty((2 * n,))
                     _lib.check(lib.pt_fourier_twiddles(n, _lib.dptr(self._tw), _lib.stream_ptr()),
@@ -411,7 +416,7 @@ class FourMat(_DiffMat):
                 d_y = self._prepare_out(d_u, out, beta)
                 rc = lib.pt_fourier_apply(_lib.dptr(self._tw), n, float(self.period), int(self.order),
                                           _lib.dptr(d_u), _lib.dptr(d_y), after, before, float(alpha),
-                                          float(beta), _lib.stream_ptr())
+                                          float(beta), _lib.dptr(d_scale), slen, _lib.stream_ptr())
                 if rc == 0:
                     return d_y
                 if rc != -3:
@@ -529,7 +534,7 @@ class PolarLaplacian:
     1/r^2 scaling fused in its epilogue (``pt_dense_apply`` with PT_SCALE_AFTER).
     """
 
-    def __init__(self, grid, radial="cheb", accuracy=6):
+    def __init__(self, grid, radial="cheb", accuracy=6, azimuthal="dense"):
         if isinstance(grid, (int, np.integer)):
             grid = getattr(_get_grid_manager(), str(int(grid)))
         if grid.num_dim != 2:
@@ -551,7 +556,8 @@ class PolarLaplacian:
         d_r = _lib.to_device(r)
         radial_mat = d2.device() + d1.device() / d_r[:, None]
         self.radial = _DiffMat._wrap(radial_mat, self.npts, 1, 2, grid.num)
-        self.azimuthal = FourMat(grid, axis=0, order=2)
+        # azimuthal="fft": D2_theta through pt_fourier_apply (1/r^2 still fused in its epilogue)
+        self.azimuthal = FourMat(grid, axis=0, order=2, method=azimuthal)
         self.inv_r2 = 1.0 / (d_r * d_r)
 
     def apply(self, u):

@@ -93,3 +93,43 @@ def test_known_answer_config2_axis():
     assert np.max(np.abs(F.apply(u) - np.cos(x) * u)) < 1e-11
     F2 = pt.FourMat(x, order=2, method="fft")
     assert np.max(np.abs(F2.apply(u) - (np.cos(x) ** 2 - np.sin(x)) * u)) < 1e-9
+
+
+def test_polar_laplacian_with_fft_azimuthal_operator():
+    """Config 3 at reduced size: lap u = (D2_r + D_r/r) u + (1/r^2) D2_theta u with D2_theta through
+    the FFT and the 1/r^2 scaling fused in its store phase (PT_SCALE_AFTER)."""
+    import pytristan_b200 as pt
+
+    pt.drop_all_grids()
+    g = pt.get_polar_grid(64, 24, axes=[1], mappers=[pt.cheb], fornberg=True)
+    lap = pt.PolarLaplacian(g, azimuthal="fft")
+    dense = pt.PolarLaplacian(g)
+    th, r = g.axpoints(0), g.axpoints(1)
+    T, R = np.asarray(g)[0], np.asarray(g)[1]
+    U = np.random.default_rng(1234).standard_normal((3, T.size))
+    y = lap.apply(U)
+    yref = oracle.polar_laplacian(th, r, U)
+    assert np.linalg.norm(y - yref) / np.linalg.norm(yref) <= 1e-12
+    assert np.linalg.norm(y - dense.apply(U)) / np.linalg.norm(yref) <= 1e-12
+    assert np.max(np.abs(lap.apply(R ** 3 * np.cos(3 * T)))) < 1e-8
+    assert np.max(np.abs(lap.apply(R ** 2) - 4.0)) < 1e-8
+    pt.drop_all_grids()
+
+
+def test_fft_after_scale_strided_axis():
+    import torch
+
+    import pytristan_b200 as pt
+
+    n, before, after = 64, 6, 5
+    x = np.arange(n) * (2 * np.pi / n)
+    F = pt.FourMat(x, order=2, method="fft")
+    F.npts, F.axis = (before, n, after), 1
+    rng = np.random.default_rng(5)
+    U = rng.standard_normal((1, before * n * after))
+    sc = rng.uniform(0.5, 2.0, after)
+    D = oracle.four_mat(n, 2 * np.pi, 2)
+    ref = oracle.apply_along_axis(D, U, F.npts, 1).reshape(after, n, before) * sc[:, None, None]
+    bound = oracle.abs_bound(D, U, F.npts, 1).reshape(after, n, before) * sc[:, None, None]
+    got = F.apply(torch.from_numpy(U).cuda(), scale=sc, scale_mode="after").cpu().numpy().reshape(after, n, before)
+    assert np.max(np.abs(got - ref) / bound) <= TOL
