@@ -56,6 +56,18 @@ def workload_spec(name):
                     ops=[("d/dx FourMat n=1024 axis0 (FFT)", "four_fft", 0, 1, 16.0 * P * BATCH),
                          ("d2/dy2 ChebMat n=257 axis1 (K1)", "cheb", 1, 2, 2.0 * NY * P * BATCH)],
                     points_per_step=2 * P * BATCH)
+    if name in ("polar_1024x512_b64", "polar_1024x512_b1", "polar_1024x512_b64_fft"):
+        # BASELINE configs[2]: polar grid, theta Fourier (1024) x r Chebyshev (get_polar_grid(1024, 256,
+        # fornberg=True): 512 mapped CGL nodes on [-1, 1], none at r = 0); one step = one Laplacian
+        # (D2_r + D_r/r) u + (1/r^2) D2_theta u = two operator applications per point
+        nt, nr = 1024, 512
+        P = nt * nr
+        b = 1 if name.endswith("_b1") else BATCH
+        kind = "polar_fft" if name.endswith("_fft") else "polar"
+        return dict(name=name, npts=(nt, nr), batch=b, bound="tensor",
+                    ops=[("polar Laplacian: radial n=512 (K1) + azimuthal n=1024 (" + ("FFT" if kind == "polar_fft" else "K2") + ", 1/r^2 fused)",
+                          kind, 0, 2, 2.0 * (nr + (0 if kind == "polar_fft" else nt)) * P * b)],
+                    points_per_step=2 * P * b)
     if name == "fd6_512cube":
         P = 512 ** 3
         return dict(name=name, npts=(512, 512, 512), batch=1, bound="hbm",
@@ -156,6 +168,14 @@ class ClockSampler:
 def cpu_operators(spec, nodes):
     from oracle import operators as oracle
 
+    if spec["ops"][0][1] in ("polar", "polar_fft"):
+        import pytristan_b200 as pt
+
+        theta = np.linspace(-np.pi, np.pi - 2 * np.pi / 1024, 1024)
+        r = pt.cheb(512, -1.0, 1.0)
+        h = (theta[-1] - theta[0]) / 1023
+        return [("polar", (oracle.four_mat(1024, 1024 * h, 2), oracle.cheb_mat(r, 2) + oracle.cheb_mat(r, 1) / r[:, None],
+                           1.0 / (r * r)))]
     mats = []
     for (_, kind, axis, order, _) in spec["ops"]:
         x = nodes[axis]
@@ -174,7 +194,13 @@ def cpu_step(spec, mats, U):
 
     outs = []
     for (kind, M), (_, _, axis, _, _) in zip(mats, spec["ops"]):
-        if kind == "dense":
+        if kind == "polar":     # oracle.polar_laplacian with the matrices built once
+            D2t, Ar, inv_r2 = M
+            nt, nr = spec["npts"]
+            Y = oracle.apply_along_axis(Ar, U, (nt, nr), 1)
+            T = oracle.apply_along_axis(D2t, U, (nt, nr), 0)
+            outs.append(Y + np.tile(np.repeat(inv_r2, nt), U.size // (nt * nr)).reshape(U.shape) * T)
+        elif kind == "dense":
             outs.append(oracle.apply_along_axis(M, U, spec["npts"], axis))
         else:
             outs.append(oracle.stencil_apply(M, U, spec["npts"], axis))
@@ -228,6 +254,10 @@ def run_reference(args, spec):
 def build_ops(spec, nodes):
     import pytristan_b200 as pt
 
+    if spec["ops"][0][1] in ("polar", "polar_fft"):
+        pt.drop_all_grids()
+        g = pt.get_polar_grid(1024, 256, axes=[1], mappers=[pt.cheb], fornberg=True)
+        return [pt.PolarLaplacian(g, azimuthal="fft" if spec["ops"][0][1] == "polar_fft" else "dense")]
     ops = []
     for (_, kind, axis, order, _) in spec["ops"]:
         x = nodes[axis]
@@ -377,7 +407,7 @@ def run_gpu(args, spec):
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        sample_b = B if spec["name"].startswith("channel_1024x257_b64") else 1
+        sample_b = B if spec["name"].startswith(("channel_1024x257_b64", "polar_")) else 1
         if spec["name"].startswith("fd6_1024"):
             cpu = {"value": None, "unit": "points/s", "cores": cores, "kind": "port",
                    "sample": "skipped: 1024^3 slice-sum oracle needs > 60 s"}

@@ -109,6 +109,9 @@ def launches_per_apply(ops, after=1):
     """Number of kernel launches one pass of ``ops`` issues (for bench.py's gpu_launches)."""
     count = 0
     for op in ops:
+        if hasattr(op, "launches"):
+            count += op.launches
+            continue
         band = getattr(op, "_band", None)
         if band is None:
             count += 1
