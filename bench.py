@@ -479,13 +479,17 @@ def run_gpu_sharded(args, spec):
             own = buf.local[:plan.nloc * n * n]
             own.view(1, plan.nloc, n * n).copy_(field)
 
+            fused = args.fused_gradient
+
             def step():
                 fab.barrier()                           # neighbours' fields are current (device flag barrier)
+                if fused and plan.gradient_peer(buf, fx, fy, n, n, outs):
+                    return                              # one read of the slab, z halo planes over NVLink
                 fx.apply(own, out=outs[0])
                 fy.apply(own, out=outs[1])
                 plan.apply_peer(buf, 1, n * n, outs[2].view(1, plan.nloc, n * n))   # halo rows loaded over NVLink
 
-            launches = 6                                # barrier + 3 stencil kernels + 2 boundary-row kernels
+            launches = 5 if fused else 6                # barrier + kernels (+ boundary-row kernels)
         else:
             ext = torch.zeros(plan.ext_shape(1, n * n), dtype=torch.float64, device="cuda")
             plan.interior(ext).copy_(field)
@@ -558,8 +562,10 @@ def run_gpu_sharded(args, spec):
         if spec["bound"] == "hbm":
             peak = peaks.get("hbm_gbs", 6650.0)
             ach = local_alg / (ms * 1e-3) * 1e-9
+            if getattr(args, "fused_gradient", False) and peer:
+                ach *= 32.0 / 48.0                      # fused gradient: 8 B/pt read + 24 B/pt written
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                    "note": "per-GPU algorithmic bytes of the whole step (3 derivatives, 16 B/pt each) over the step time, halo exchange included"}
+                    "note": "per-GPU algorithmic bytes of the whole step (3 derivatives: 16 B/pt each, or 32 B/pt for the fused gradient) over the step time, halo traffic included"}
         else:
             ach = local_alg / (ms * 1e-3) * 1e-12
             roof = {"bound": "tensor", "achieved": ach, "peak": 37.0, "unit": "TFLOP/s", "frac": ach / 37.0, "traffic": None,
@@ -570,7 +576,7 @@ def run_gpu_sharded(args, spec):
                 "config": {"workload": spec["name"], "npts": list(spec["npts"]), "ops": [o[0] for o in spec["ops"]],
                            "sharding": ("z slabs, " + ("halo rows loaded from the neighbours' memory (peer loads, device flag barrier)" if peer else "halo exchange (NCCL send/recv)")) if spec["kind"] == "slab"
                            else ("2-D pencils, " + ("redistribution fused into the DMMA epilogue / peer-store scatter over NVLink, device flag barriers" if peer else "pack + all_to_all + unpack")),
-                           "comm": args.comm,
+                           "comm": args.comm, "fused_gradient": bool(args.fused_gradient and peer and spec["kind"] == "slab"),
                            "l2": "per-rank field larger than L2" if host_bytes > 126e6 else "per-rank field fits L2 (strong scaling)"},
                 "roofline": roof, "cpu_baseline": None,
                 "e2e": None, "gpu_launches": args.steps * launches * world, "clocks": sampler.summary()}
@@ -590,6 +596,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="channel_1024x257_b64")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--fused-gradient", action="store_true",
+                    help="slab workload: the three derivatives in one read of the field (pt_stencil_grad3_halo)")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="sharded workloads: peer-memory kernels (default) or the NCCL exchange/all_to_all path")
     args = ap.parse_args()

@@ -186,6 +186,16 @@ int pt_stencil_grad3(const double* U, double* GX, double* GY, double* GZ, int nx
                      int64_t nfields, const double* const* W, const int32_t* const* start,
                      const int* wmax, const pt_uniform_rows* const* uni, pt_stream_t stream);
 
+/* The same fused gradient on a z-slab of a slab-sharded field (multi-GPU): the floor(w/2) planes
+ * below / above the nz_own local planes are loaded from the neighbours' memory (U_lo points at
+ * the first of them in the lower neighbour, U_hi at the upper neighbour's first plane; NULL = no
+ * neighbour, i.e. a physical boundary with one-sided rows).  The z band (W[2], start[2], uni[2])
+ * describes the LOCAL rows, start relative to the virtual slab as in pt_stencil_apply_halo. */
+int pt_stencil_grad3_halo(const double* U, const double* U_lo, const double* U_hi, double* GX,
+                          double* GY, double* GZ, int nx, int ny, int nz_own, const double* const* W,
+                          const int32_t* const* start, const int* wmax,
+                          const pt_uniform_rows* const* uni, pt_stream_t stream);
+
 /* ---- K7: pencil-transpose pack/unpack (multi-GPU) ----------------------------------------- */
 /* Generic 3-D permutation copy used on both sides of the all-to-all: in is (d2, d1, d0)
  * C-contiguous; out[perm] = in, perm one of the 6 axis orders encoded as p0 + 3*p1 + 9*p2

@@ -389,8 +389,16 @@ int g_dense_config = -1;  // tuning hook (pt_debug_set_dense_config); -1 = choos
 int g_dense_atma = 0;     // tuning hook (pt_debug_set_dense_tma(2)): operator panels via cp.async.bulk
 int g_dense_tma = 0;      // tuning hook (pt_debug_set_dense_tma): 1 = persistent TMA/mbarrier kernel
 
+// CTAs the large tiles would launch: below one per SM the GPU is mostly idle (single fields:
+// BASELINE config 3 at B = 1), so the small 64x32 tile (config 2) is used to fill it
+int64_t ctas_of(const DenseParams& p, int bm, int bn) {
+  const int64_t mb = (p.n_out + bm - 1) / bm, nb = (p.NN + bn - 1) / bn;
+  return mb * nb;
+}
+
 int choose_config(const DenseParams& p) {
   if (g_dense_config >= 0) return g_dense_config;
+  if (ctas_of(p, 96, 64) < pt::sm_count()) return 2;
   // measured on B200 (tools/sweep_dense.py, profiles/r01_dense_config_sweep.md): the 96x64 tile
   // with 3 CTAs/SM wins everywhere except when n_out is a large multiple of 128, where the
   // 128x64 tile with 2 CTAs/SM has no ragged last block and slightly better operand reuse
@@ -409,6 +417,8 @@ int launch_shape(DenseParams& p, cudaStream_t stream) {
     return launch_cfg<1, 4, 12, 2, 4, 3, KCONTIG, VEC16, 3, true>(p, stream);
   }
   switch (cfg) {
+    case 2: return launch_cfg<2, 2, 4, 2, 4, 4, KCONTIG, VEC16, 4>(p, stream);   // 32x16 per warp,  64x32 CTA, 4 CTAs/SM
+    case 3: return launch_cfg<2, 2, 4, 4, 4, 4, KCONTIG, VEC16, 4>(p, stream);   // 32x32 per warp,  64x64 CTA, 4 CTAs/SM
     case 5: return launch_cfg<2, 2, 8, 4, 4, 4, KCONTIG, VEC16, 2>(p, stream);   // 64x32 per warp, 128x64 CTA, 2 CTAs/SM
     default: return launch_cfg<1, 4, 12, 2, 4, 3, KCONTIG, VEC16, 3>(p, stream); // 96x16 per warp,  96x64 CTA, 3 CTAs/SM
   }

@@ -519,6 +519,10 @@ namespace {
 
 struct Grad3Params {
   const double* __restrict__ U;
+  // peer-halo form: the HW planes below z = 0 / above z = nz - 1 live in the neighbours' memory
+  // (Ulo points at plane -HW, Uhi at plane nz); nullptr = no neighbour (physical boundary)
+  const double* __restrict__ Ulo;
+  const double* __restrict__ Uhi;
   double* __restrict__ G[3];
   int nx, ny, nz;
   int zchunk;
@@ -544,7 +548,16 @@ __global__ void __launch_bounds__(32 * TY, 1024 / (32 * TY)) stencil_grad3_kerne
   const int64_t plane = int64_t(p.nx) * p.ny;
   const bool mine = (x0 < p.nx) && (y < p.ny);            // nx is even: x0 + 1 < nx as well
   const double2 zero2 = make_double2(0.0, 0.0);
-  const double* up = p.U + int64_t(y) * p.nx + x0;         // + z*plane
+  const int64_t col = int64_t(y) * p.nx + x0;
+  // the two x-adjacent points of this thread in plane z; planes outside the slab come from the
+  // neighbours (peer loads) or are zero
+  auto ldz = [&](int z) -> double2 {
+    const double* base;
+    if (z < 0) base = p.Ulo ? p.Ulo + (z + HW) * plane : nullptr;
+    else if (z >= p.nz) base = p.Uhi ? p.Uhi + (z - p.nz) * plane : nullptr;
+    else base = p.U + z * plane;
+    return (mine && base) ? *reinterpret_cast<const double2*>(base + col) : zero2;
+  };
 
   // halo duty: 2*(TY) x-halo row pieces (2 double2 left, 2 right per row) + 2*HW full rows
   constexpr int XH = TY * 4;                 // double2 chunks of the x halos
@@ -577,15 +590,11 @@ __global__ void __launch_bounds__(32 * TY, 1024 / (32 * TY)) stencil_grad3_kerne
 
   double2 win[W];
 #pragma unroll
-  for (int s = 0; s < W - 1; ++s) {
-    const int z = z0 - HW + s;
-    win[s] = (mine && z >= 0 && z < p.nz) ? *reinterpret_cast<const double2*>(up + z * plane) : zero2;
-  }
+  for (int s = 0; s < W - 1; ++s) win[s] = ldz(z0 - HW + s);
   double2 hreg = (h_ok) ? *reinterpret_cast<const double2*>(p.U + z0 * plane + h_off) : zero2;
 
   for (int z = z0; z < z1; ++z) {
-    const int zn = z + HW;
-    win[W - 1] = (mine && zn < p.nz) ? *reinterpret_cast<const double2*>(up + zn * plane) : zero2;
+    win[W - 1] = ldz(z + HW);
     double* buf = sm[z & 1];
     *reinterpret_cast<double2*>(buf + (ty + HW) * PITCH + HX + 2 * tx) = win[HW];
     if (h_sm >= 0) {
@@ -614,9 +623,10 @@ __global__ void __launch_bounds__(32 * TY, 1024 / (32 * TY)) stencil_grad3_kerne
         gz2.y = fma(wz[s], win[s].y, gz2.y);
       }
       const int64_t o = z * plane + int64_t(y) * p.nx + x0;
-      *reinterpret_cast<double2*>(p.G[0] + o) = gx2;
-      *reinterpret_cast<double2*>(p.G[1] + o) = gy2;
-      *reinterpret_cast<double2*>(p.G[2] + o) = gz2;
+      // streaming stores: the outputs are never re-read, keep L2 for the halo re-reads of U
+      __stcs(reinterpret_cast<double2*>(p.G[0] + o), gx2);
+      __stcs(reinterpret_cast<double2*>(p.G[1] + o), gy2);
+      __stcs(reinterpret_cast<double2*>(p.G[2] + o), gz2);
     }
 #pragma unroll
     for (int s = 0; s < W - 1; ++s) win[s] = win[s + 1];
@@ -644,9 +654,10 @@ extern "C" int pt_debug_set_grad_ty(int ty) {
   return PT_OK;
 }
 
-extern "C" int pt_stencil_grad3(const double* U, double* GX, double* GY, double* GZ, int nx, int ny, int nz,
-                                int64_t nfields, const double* const* W, const int32_t* const* start,
-                                const int* wmax, const pt_uniform_rows* const* uni, pt_stream_t stream) {
+namespace {
+int grad3_impl(const double* U, const double* U_lo, const double* U_hi, double* GX, double* GY, double* GZ,
+               int nx, int ny, int nz, int64_t nfields, const double* const* W, const int32_t* const* start,
+               const int* wmax, const pt_uniform_rows* const* uni, pt_stream_t stream) {
   PT_REQUIRE(U && GX && GY && GZ && W && start && wmax && uni, "pt_stencil_grad3: null pointer");
   PT_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1 && nfields >= 0, "pt_stencil_grad3: bad shape");
   PT_REQUIRE(U != GX && U != GY && U != GZ, "pt_stencil_grad3: in-place application is not supported");
@@ -657,7 +668,10 @@ extern "C" int pt_stencil_grad3(const double* U, double* GX, double* GY, double*
     if (k == 0) w = uni[k]->w_uni;
     if (uni[k]->w_uni != w) return pt::fail(PT_ERR_UNSUPPORTED, "pt_stencil_grad3: stencil widths differ");
     const int hw = w / 2;
-    if (uni[k]->lo != hw || uni[k]->hi != dims[k] - hw || dims[k] < 2 * w)
+    // canonical rows: everything but the hw rows next to a physical boundary (a slab side with a
+    // neighbour has no boundary rows)
+    const int lo_k = (k == 2 && U_lo) ? 0 : hw, hi_k = (k == 2 && U_hi) ? dims[k] : dims[k] - hw;
+    if (uni[k]->lo != lo_k || uni[k]->hi != hi_k || dims[k] < 2 * w)
       return pt::fail(PT_ERR_UNSUPPORTED, "pt_stencil_grad3: axis %d is not a plain non-periodic uniform axis", k);
     PT_REQUIRE(W[k] && start[k] && wmax[k] >= 1 && wmax[k] <= MAXW, "pt_stencil_grad3: bad band for axis %d", k);
   }
@@ -670,6 +684,7 @@ extern "C" int pt_stencil_grad3(const double* U, double* GX, double* GY, double*
   for (int64_t f = 0; f < nfields; ++f) {
     Grad3Params p;
     p.U = U + f * P;
+    p.Ulo = U_lo; p.Uhi = U_hi;
     for (int k = 0; k < 3; ++k) {
       p.G[k] = G[k] + f * P;
       for (int s = 0; s < MAXW; ++s) p.w[k][s] = s < w ? uni[k]->wuni[s] : 0.0;
@@ -701,9 +716,31 @@ extern "C" int pt_stencil_grad3(const double* U, double* GX, double* GY, double*
       q.periodic = 0; q.alpha = 1.0; q.beta = 0.0;
       q.lo = uni[k]->lo; q.hi = uni[k]->hi;
       q.Ulo = nullptr; q.Uhi = nullptr; q.halo_lo = 0; q.halo_hi = 0; q.lo_stride = 0; q.hi_stride = 0;
+      if (k == 2 && (U_lo || U_hi)) {
+        // start[] of a slab is relative to the virtual slab (halo rows first): the table reads
+        // them from wherever they live
+        const int hw = w / 2;
+        q.halo_lo = U_lo ? hw : 0; q.halo_hi = U_hi ? hw : 0;
+        q.Ulo = U_lo ? U_lo : p.U; q.Uhi = U_hi ? U_hi : p.U;
+        q.n = q.halo_lo + nz + q.halo_hi; q.shift = q.halo_lo;
+      }
       rc = launch_table(q, q.lo, q.hi, st);
       if (rc) return rc;
     }
   }
   return PT_OK;
+}
+}  // namespace
+
+extern "C" int pt_stencil_grad3(const double* U, double* GX, double* GY, double* GZ, int nx, int ny, int nz,
+                                int64_t nfields, const double* const* W, const int32_t* const* start,
+                                const int* wmax, const pt_uniform_rows* const* uni, pt_stream_t stream) {
+  return grad3_impl(U, nullptr, nullptr, GX, GY, GZ, nx, ny, nz, nfields, W, start, wmax, uni, stream);
+}
+
+extern "C" int pt_stencil_grad3_halo(const double* U, const double* U_lo, const double* U_hi, double* GX,
+                                     double* GY, double* GZ, int nx, int ny, int nz_own, const double* const* W,
+                                     const int32_t* const* start, const int* wmax,
+                                     const pt_uniform_rows* const* uni, pt_stream_t stream) {
+  return grad3_impl(U, U_lo, U_hi, GX, GY, GZ, nx, ny, nz_own, 1, W, start, wmax, uni, stream);
 }

@@ -240,6 +240,46 @@ class SlabStencil:
         return out
 
 
+    def gradient_peer(self, buf, fx, fy, nx, ny, outs):
+        """Fused ``(d/dx, d/dy, d/dz)`` of this rank's slab of the field in ``buf`` (``peer_field``
+        with one field): one read of the slab (``pt_stencil_grad3_halo``), the z halo planes loaded
+        from the neighbours.  ``fx``/``fy``: uniform non-periodic ``FinDiffMat``s of the x and y axes
+        with the same stencil width as this plan's; ``outs``: three CUDA tensors of the slab size.
+        Returns False (nothing done) when the fused kernel does not cover the configuration."""
+        lib = _lib.load()
+        bz = self.band
+        if self.periodic or bz.get("wuni") is None:
+            return False
+        if "uni" not in bz:
+            bz["uni"] = _lib.uniform_rows(bz, self.nloc)
+        bands = []
+        for op, n in ((fx, nx), (fy, ny)):
+            b = op._band
+            if b is None or b["wuni"] is None or b["periodic"]:
+                return False
+            if "uni" not in b:
+                b["uni"] = _lib.uniform_rows(b, n)
+            bands.append(b)
+        bands.append(bz)
+        plane = nx * ny
+        u_lo = u_hi = None
+        if self.halo_lo:
+            u_lo = ctypes.c_void_p(buf.ptrs[self.rank - 1] + 8 * (buf.rows[self.rank - 1] - self.halo_lo) * plane)
+        if self.halo_hi:
+            u_hi = ctypes.c_void_p(buf.ptrs[self.rank + 1])
+        w_arr = (ctypes.c_void_p * 3)(*[b["d_w"].data_ptr() for b in bands])
+        s_arr = (ctypes.c_void_p * 3)(*[b["d_start"].data_ptr() for b in bands])
+        m_arr = (ctypes.c_int * 3)(*[int(b["wmax"]) for b in bands])
+        u_arr = (ctypes.POINTER(_lib.UniformRows) * 3)(*[ctypes.pointer(b["uni"]) for b in bands])
+        rc = lib.pt_stencil_grad3_halo(ctypes.c_void_p(buf.ptrs[self.rank]), u_lo, u_hi, _lib.dptr(outs[0]),
+                                       _lib.dptr(outs[1]), _lib.dptr(outs[2]), nx, ny, self.nloc, w_arr, s_arr,
+                                       m_arr, u_arr, _lib.stream_ptr())
+        if rc == -3:
+            return False
+        _lib.check(rc, "pt_stencil_grad3_halo")
+        return True
+
+
 # ---- pencil decomposition -----------------------------------------------------------------------------
 class PencilTranspose:
     """Redistributions of a 3-D field ``(nz, ny, nx)`` (x fastest) over a ``py x pz`` process grid.

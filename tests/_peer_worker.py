@@ -86,6 +86,34 @@ def main():
             failures.append(("slab_peer != slab_exchange bits", order, acc, periodic, mapped))
         fab.barrier()
 
+    # ---- fused gradient of a slab-sharded field (one read, z halos from the neighbours) -----------------
+    gx_n, gy_n, gz_n = 16, 18, 14 * world
+    axes = [np.linspace(0.0, 1.0, m) for m in (gx_n, gy_n, gz_n)]
+    fops = []
+    for k in range(3):
+        F = pt.FinDiffMat(axes[k], order=1, accuracy=6)
+        F.npts, F.axis = (gx_n, gy_n, gz_n), k
+        fops.append(F)
+    G = rng.standard_normal((gz_n, gy_n * gx_n))
+    plan = D.SlabStencil.from_operator(fops[2], rank, world)
+    buf = plan.peer_field(fab, 1, gy_n * gx_n)
+    buf.local[:plan.nloc * gy_n * gx_n].view(plan.nloc, gy_n * gx_n).copy_(torch.from_numpy(G[plan.z0:plan.z1]).cuda())
+    fab.barrier()
+    outs = [torch.full((plan.nloc * gy_n * gx_n,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(3)]
+    if not plan.gradient_peer(buf, fops[0], fops[1], gx_n, gy_n, outs):
+        failures.append(("gradient_peer declined",))
+    full = pt.gradient(fops, torch.from_numpy(G).cuda().reshape(-1))          # single-device fused kernel
+    for k in range(3):
+        band = oracle.findiff_band(axes[k], 1, 6)
+        ref = oracle.stencil_apply(band, G.reshape(1, -1), (gx_n, gy_n, gz_n), k).reshape(gz_n, -1)[plan.z0:plan.z1]
+        got = outs[k].cpu().numpy().reshape(plan.nloc, -1)
+        err = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
+        if not err <= 1e-12:
+            failures.append(("gradient_peer", k, float(err)))
+        if not np.array_equal(got, full[k].cpu().numpy().reshape(gz_n, -1)[plan.z0:plan.z1]):
+            failures.append(("gradient_peer != single-device bits", k))
+    fab.barrier()
+
     # ---- pencils over peer memory -----------------------------------------------------------------------
     for (py, pz) in sorted({(world, 1), (1, world), (2 if world % 2 == 0 else 1, world // (2 if world % 2 == 0 else 1))}):
         for batch in (1, 2):

@@ -108,6 +108,20 @@ if __name__ == "__main__":
             dense((512, 512, 512), 1, 1, "cfg5b y K1 n=512")
             dense((64, 4096), 0, 1, "K2 n=64")
         lib.pt_debug_set_dense_tma(ctypes.c_int(0))
+    if what == "small":
+        lib = _lib.load()
+        lib.pt_debug_set_dense_config.argtypes = [__import__("ctypes").c_int]
+        for cfg in (9, 5, 2, 3, -1):
+            lib.pt_debug_set_dense_config(cfg)
+            print("== dense config", cfg)
+            dense((1024, 512), 1, 1, "cfg3 B=1 radial K1 n=512")
+            dense((1024, 512), 0, 1, "cfg3 B=1 azimuthal K2 n=1024")
+            dense((1024, 1024), 1, 1, "cfg3 fornberg B=1 radial K1 n=1024")
+            dense((1024, 257), 1, 1, "cfg2 B=1 K1 n=257")
+            dense((1024, 257), 0, 1, "cfg2 B=1 K2 n=1024")
+            dense((64,), 0, 1, "cfg1 n=64 one field")
+            dense((256, 256), 0, 1, "256x256 K2")
+        sys.exit(0)
     if what == "tune":
         lib = _lib.load()
         lib.pt_debug_set_dense_config.argtypes = [__import__("ctypes").c_int]
