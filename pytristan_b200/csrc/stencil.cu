@@ -529,18 +529,18 @@ struct Grad3Params {
   double w[3][MAXW];
 };
 
-template <int W, int TY>
-__global__ void __launch_bounds__(32 * TY, 1024 / (32 * TY)) stencil_grad3_kernel(const Grad3Params p) {
+template <int W, int TY, int TXT>
+__global__ void __launch_bounds__(TXT * TY, 1024 / (TXT * TY)) stencil_grad3_kernel(const Grad3Params p) {
   constexpr int HW = W / 2;
   constexpr int HX = 4;              // x halo in doubles (even: keeps 16-byte alignment)
-  constexpr int TXP = 64;            // tile: 64 points in x (32 threads x double2), TY rows in y
+  constexpr int TXP = 2 * TXT;       // tile: TXT threads x double2 in x, TY rows in y
   constexpr int PITCH = TXP + 2 * HX;
   constexpr int ROWS = TY + 2 * HW;
   constexpr int PLANE = ROWS * PITCH;
   __shared__ __align__(16) double sm[2][PLANE];
 
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int tid = ty * 32 + tx;
+  const int tid = ty * TXT + tx;
   const int xb = blockIdx.x * TXP, yb = blockIdx.y * TY;
   const int x0 = xb + 2 * tx, y = yb + ty;
   const int z0 = blockIdx.z * p.zchunk;
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(32 * TY, 1024 / (32 * TY)) stencil_grad3_kerne
   // halo duty: 2*(TY) x-halo row pieces (2 double2 left, 2 right per row) + 2*HW full rows
   constexpr int XH = TY * 4;                 // double2 chunks of the x halos
   constexpr int YH = 2 * HW * (PITCH / 2);   // double2 chunks of the y halo rows
-  static_assert(XH + YH <= 32 * TY, "one halo chunk per thread");
+  static_assert(XH + YH <= TXT * TY, "one halo chunk per thread");
   int h_sm = -1;
   int64_t h_off = 0;
   bool h_ok = false;
@@ -633,24 +633,39 @@ __global__ void __launch_bounds__(32 * TY, 1024 / (32 * TY)) stencil_grad3_kerne
   }
 }
 
-int g_grad_ty = 16;  // tuning hook (pt_debug_set_grad_ty): 16 measured fastest at 1024^3
+// tile shape, tuning hook pt_debug_set_grad_ty(ty) / (ty + 100 for 64 threads along x).  Measured at
+// 1024^3 on B200: 128 x 8 points (1 KB rows = one DRAM page per tile row) 6.55 ms, 128 x 16 6.83 ms,
+// 64 x 16 7.20 ms, 64 x 32 7.49 ms
+int g_grad_ty = 8;
+int g_grad_tx = 64;  // threads along x (the tile is twice as wide)
+
+inline int grad_tile_x() { return 2 * g_grad_tx; }   // (9-point stencils use 64; only the z-chunk heuristic sees the difference)
 
 template <int W>
 int launch_grad3(const Grad3Params& p, cudaStream_t st) {
-  const int ty = g_grad_ty;
-  const int gx = (p.nx + 63) / 64, gy = (p.ny + ty - 1) / ty;
+  const int tx = (W > 7) ? 32 : g_grad_tx;        // the 128-wide tile of a 9-point stencil exceeds 48 KB
+  const int ty = (W > 7 && g_grad_ty == 8) ? 16 : g_grad_ty;
+  const int gx = (p.nx + 2 * tx - 1) / (2 * tx), gy = (p.ny + ty - 1) / ty;
   const int gz = (p.nz + p.zchunk - 1) / p.zchunk;
   if (gy > 65535 || gz > 65535) return pt::fail(PT_ERR_UNSUPPORTED, "pt_stencil_grad3: grid too large");
-  dim3 grid(gx, gy, gz), block(32, ty);
-  if (ty == 32) stencil_grad3_kernel<W, 32><<<grid, block, 0, st>>>(p);
-  else stencil_grad3_kernel<W, 16><<<grid, block, 0, st>>>(p);
+  dim3 grid(gx, gy, gz), block(tx, ty);
+  if constexpr (W <= 7) {
+    if (tx == 64) {
+      if (ty == 8) stencil_grad3_kernel<W, 8, 64><<<grid, block, 0, st>>>(p);
+      else stencil_grad3_kernel<W, 16, 64><<<grid, block, 0, st>>>(p);
+      return pt::check_launch("pt_stencil_grad3");
+    }
+  }
+  if (ty == 32) stencil_grad3_kernel<W, 32, 32><<<grid, block, 0, st>>>(p);
+  else stencil_grad3_kernel<W, 16, 32><<<grid, block, 0, st>>>(p);
   return pt::check_launch("pt_stencil_grad3");
 }
 
 }  // namespace
 
 extern "C" int pt_debug_set_grad_ty(int ty) {
-  g_grad_ty = (ty == 16) ? 16 : 32;
+  if (ty >= 100) { g_grad_tx = 64; g_grad_ty = (ty - 100 == 16) ? 16 : 8; }
+  else { g_grad_tx = 32; g_grad_ty = (ty == 16) ? 16 : 32; }
   return PT_OK;
 }
 
@@ -691,7 +706,7 @@ int grad3_impl(const double* U, const double* U_lo, const double* U_hi, double* 
     }
     p.nx = nx; p.ny = ny; p.nz = nz;
     // z-chunks: enough CTAs for a few waves, halo re-read (w-1 planes per chunk) kept small
-    const int64_t tiles = int64_t((nx + 63) / 64) * ((ny + g_grad_ty - 1) / g_grad_ty);
+    const int64_t tiles = int64_t((nx + grad_tile_x() - 1) / grad_tile_x()) * ((ny + g_grad_ty - 1) / g_grad_ty);
     int chunks = int((int64_t(pt::sm_count()) * 8 + tiles - 1) / tiles);
     if (chunks < 1) chunks = 1;
     int zchunk = (nz + chunks - 1) / chunks;
