@@ -396,6 +396,33 @@ def test_fused_gradient(npts, accuracy):
     assert np.max(np.abs(got[1].cpu().numpy() - ref)) <= 1e-12 * np.max(np.abs(ref))
 
 
+@pytest.mark.parametrize("tile", [16, 32, 108, 116])
+def test_fused_gradient_tile_shapes_agree_bitwise(tile):
+    """Every tile shape of pt_stencil_grad3 (64x16, 64x32, 128x8, 128x16 points) performs the same
+    per-point arithmetic: results must be bit-identical to the default shape's."""
+    import pytristan_b200 as pt
+    from pytristan_b200 import _lib
+
+    torch = _torch()
+    npts = (150, 37, 29)
+    axes = [np.linspace(0.0, 1.0 + k, n) for k, n in enumerate(npts)]
+    ops = []
+    for k in range(3):
+        F = pt.FinDiffMat(axes[k], order=1, accuracy=6)
+        F.npts, F.axis = npts, k
+        ops.append(F)
+    U = torch.from_numpy(np.random.default_rng(7).standard_normal(int(np.prod(npts)))).cuda()
+    lib = _lib.load()
+    ref = [g.clone() for g in pt.gradient(ops, U)]
+    try:
+        lib.pt_debug_set_grad_ty(tile)
+        got = pt.gradient(ops, U)
+        for k in range(3):
+            assert torch.equal(got[k], ref[k]), (tile, k)
+    finally:
+        lib.pt_debug_set_grad_ty(108)         # default: 128 x 8
+
+
 # ---------------------------------------------------------------------------------------------
 # collocation on non-affinely mapped nodes; Fourier orders > 2
 # ---------------------------------------------------------------------------------------------
