@@ -257,6 +257,18 @@ int pt_stencil_apply_halo(const double* W, const int32_t* start, int wmax, int n
                           int64_t before, const pt_uniform_rows* uni, double alpha, double beta,
                           pt_stream_t stream);
 
+/* ---- boundary rows and solves along an axis ---------------------------- */
+/* Rows rows[r] (r < nrows) of the n*n row-major device matrix D are overwritten by R[r] (nrows*n):
+ * boundary-condition row replacement (Dirichlet: identity rows; Neumann/Robin: rows of D1, ...). */
+int pt_replace_rows(double* D, int n, const int32_t* rows, int nrows, const double* R,
+                    pt_stream_t stream);
+/* Ainv = A^-1 (n*n row-major, n <= 4096) by Gauss-Jordan elimination with partial pivoting in FP64.
+ * work: pt_invert_work_size(n) doubles.  *info (device int32) is 0 on success, c+1 if the matrix is
+ * exactly singular at elimination step c.  A solve A y = f along a grid axis, for all grid lines
+ * at once, is then pt_dense_apply with the packed inverse. */
+int64_t pt_invert_work_size(int n);
+int pt_invert(const double* A, int n, double* Ainv, double* work, int32_t* info, pt_stream_t stream);
+
 /* ---- measurement helper ------------------------------------------------------------------ */
 /* Register-resident DMMA loop: the FP64 tensor-core roofline denominator measured on the box.
  * Writes achieved TFLOP/s to *tflops_host. */
