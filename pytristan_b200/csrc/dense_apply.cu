@@ -315,8 +315,8 @@ dense_apply_kernel(const DenseParams p) {
       if (row >= p.n_out) continue;
       double r0 = s0, r1 = s1;
       if (p.scale_mode == PT_SCALE_ROW) { const double sr = p.scale[row]; r0 *= sr; r1 *= sr; }
-      double v0 = r0 * acc[i][j][0];
-      double v1 = r1 * acc[i][j][1];
+      double v0 = __dmul_rn(r0, acc[i][j][0]);   // explicit roundings: every kernel variant gives the same bits
+      double v1 = __dmul_rn(r1, acc[i][j][1]);
       const int64_t off = int64_t(row) * p.before;
       const double* c0 = (SCAT ? p.C : p.Y) + l0 + off;
       const double* c1 = (SCAT ? p.C : p.Y) + l1 + off;
@@ -330,13 +330,13 @@ dense_apply_kernel(const DenseParams p) {
       }
       if (!KCONTIG && VEC16) {
         // before is even and nn is even: both columns are adjacent in the same slab
-        if (use_beta) { const double2 o = *reinterpret_cast<const double2*>(c0); v0 += p.beta * o.x; v1 += p.beta * o.y; }
+        if (use_beta) { const double2 o = *reinterpret_cast<const double2*>(c0); v0 = __fma_rn(p.beta, o.x, v0); v1 = __fma_rn(p.beta, o.y, v1); }
         *reinterpret_cast<double2*>(y0) = make_double2(v0, v1);
       } else {
-        if (use_beta) v0 += p.beta * *c0;
+        if (use_beta) v0 = __fma_rn(p.beta, *c0, v0);
         *y0 = v0;
         if (two) {
-          if (use_beta) v1 += p.beta * *c1;
+          if (use_beta) v1 = __fma_rn(p.beta, *c1, v1);
           *y1 = v1;
         }
       }

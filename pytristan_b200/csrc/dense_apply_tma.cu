@@ -228,18 +228,18 @@ dense_apply_tma_kernel(const DenseParams p, int64_t tiles_total) {
         if (row >= p.n_out) continue;
         double r0 = s0, r1 = s1;
         if (p.scale_mode == PT_SCALE_ROW) { const double sr = p.scale[row]; r0 *= sr; r1 *= sr; }
-        double v0 = r0 * acc[i][j][0];
-        double v1 = r1 * acc[i][j][1];
+        double v0 = __dmul_rn(r0, acc[i][j][0]);   // explicit roundings: every kernel variant gives the same bits
+        double v1 = __dmul_rn(r1, acc[i][j][1]);
         const int64_t off = int64_t(row) * p.before;
         if (!KCONTIG) {
           double2* dst = reinterpret_cast<double2*>(y0 + off);
-          if (use_beta) { const double2 o = *dst; v0 += p.beta * o.x; v1 += p.beta * o.y; }
+          if (use_beta) { const double2 o = *dst; v0 = __fma_rn(p.beta, o.x, v0); v1 = __fma_rn(p.beta, o.y, v1); }
           *dst = make_double2(v0, v1);
         } else {
-          if (use_beta) v0 += p.beta * y0[off];
+          if (use_beta) v0 = __fma_rn(p.beta, y0[off], v0);
           y0[off] = v0;
           if (two) {
-            if (use_beta) v1 += p.beta * y1[off];
+            if (use_beta) v1 = __fma_rn(p.beta, y1[off], v1);
             y1[off] = v1;
           }
         }

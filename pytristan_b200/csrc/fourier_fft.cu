@@ -385,7 +385,6 @@ int launch_fft(FftParams& p, cudaStream_t st) {
   const int cfg = g_fft_config >= 0 ? g_fft_config : ((LOG2N == 10 && !STRIDED) ? 1 : 0);
   switch (cfg) {
     case 0: return launch_fft_cfg<LOG2N, STRIDED, 256, 4096>(p, st);
-    case 2: return launch_fft_cfg<LOG2N, STRIDED, 128, 4096>(p, st);
     default: return launch_fft_cfg<LOG2N, STRIDED, 128, 2048>(p, st);
   }
 }

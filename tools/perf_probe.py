@@ -77,7 +77,7 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what == "fftcfg":
         lib = _lib.load()
-        for cfg in (0, 1, 2):
+        for cfg in (0, 1):
             lib.pt_debug_set_fft_config(cfg)
             print("== fft config", cfg)
             fourier((1024, 257), 0, 64, "cfg2 d/dx FourMat n=1024 axis0")
