@@ -417,6 +417,7 @@ class PencilPeer(PencilTranspose):
         for name, bufB, bufC in (("u", self.uB, self.uC), ("acc", self.accB, self.accC)):
             self.maps[name + "_AB"] = fabric.scatter_map(bufB, row, *self.map_ab())
             self.maps[name + "_BC"] = fabric.scatter_map(bufC, col, *self.map_bc())
+        self._back = None     # buffers of the way back (layout C -> B -> A), allocated on first use
 
     # destination maps as (chunk, a_inner, s_outer, s_inner, s_i, offset); see pt_scatter_map
     def map_ab(self):
@@ -427,6 +428,34 @@ class PencilPeer(PencilTranspose):
         """Layout B ``(batch*nzl, ny, nxl)`` -> layout C ``(batch, nz, nyl2, nxl)`` of the rank owning y // nyl2."""
         blk = self.nyl2 * self.nxl
         return (self.nyl2, self.nzl, self.nz * blk, blk, self.nxl, self.rz * self.nzl * blk)
+
+    def map_cb(self):
+        """Layout C ``(batch, nz, nyl2*nxl)`` -> layout B ``(batch*nzl, ny, nxl)`` of the rank owning z // nzl."""
+        return (self.nzl, 1, self.nzl * self.ny * self.nxl, 0, self.ny * self.nxl, self.rz * self.nyl2 * self.nxl)
+
+    def map_ba(self):
+        """Layout B ``(lead, ny, nxl)`` -> layout A ``(lead, nyl, nx)`` of the rank owning y // nyl."""
+        return (self.nyl, 1, self.nyl * self.nx, 0, self.nx, self.ry * self.nxl)
+
+    def to_layout_a(self, c_block):
+        """Redistribute a layout-C block (e.g. the result of ``apply_sum``) back to layout A
+        ``(batch, nzl, nyl, nx)``: two peer-store scatters and two barriers (collective: every rank
+        must call it).  Returns a view of a symmetric buffer, valid until the next call."""
+        lib = _lib.load()
+        fab = self.fabric
+        if self._back is None:                       # collective allocation on first use
+            bB, bA = fab.alloc(self.count), fab.alloc(self.count)
+            self._back = (bB, bA, fab.scatter_map(bB, self.col_ranks, *self.map_cb()),
+                          fab.scatter_map(bA, self.row_ranks, *self.map_ba()))
+        bB, bA, m_cb, m_ba = self._back
+        lead = self.batch * self.nzl
+        _lib.check(lib.pt_peer_scatter(_lib.dptr(c_block.reshape(-1)), self.nz, self.batch, self.nyl2 * self.nxl,
+                                       ctypes.byref(m_cb), _lib.stream_ptr()), "pt_peer_scatter")
+        fab.barrier()
+        _lib.check(lib.pt_peer_scatter(_lib.dptr(bB.local), self.ny, lead, self.nxl, ctypes.byref(m_ba),
+                                       _lib.stream_ptr()), "pt_peer_scatter")
+        fab.barrier()
+        return bA.local.view(self.batch, self.nzl, self.nyl, self.nx)
 
     def apply_sum(self, ops, u):
         """``sum_k ops[k] along axis k`` of the field whose layout-A block is ``u``

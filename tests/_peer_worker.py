@@ -136,6 +136,11 @@ def main():
             err = np.max(np.abs(res - ref[sl]) / scale[sl])
             if not err <= 1e-12:
                 failures.append(("pencil_peer", py, pz, batch, float(err)))
+            # the way back: layout C -> B -> A
+            back = pp.to_layout_a(pp.apply_sum(mats, u)).cpu().numpy()
+            sla = (slice(None), slice(rz * pp.nzl, (rz + 1) * pp.nzl), slice(ry * pp.nyl, (ry + 1) * pp.nyl), slice(None))
+            if not np.max(np.abs(back - ref[sla]) / scale[sla]) <= 1e-12:
+                failures.append(("pencil_peer to_layout_a", py, pz, batch))
             # single-device computation of the same sum: must agree bit for bit (same summation order)
             Gd = torch.from_numpy(G).cuda()
             full = mats[0]._apply_device(Gd.reshape(-1), batch * NZ * NY, NX, 1, None, 1.0, 0.0, None, None)

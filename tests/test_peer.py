@@ -73,6 +73,31 @@ def test_scatter_maps_reproduce_the_pencil_layouts(py, pz, batch):
         want = G[:, :, pp.rz * pp.nyl2:(pp.rz + 1) * pp.nyl2, pp.ry * pp.nxl:(pp.ry + 1) * pp.nxl]
         np.testing.assert_array_equal(bufC[r].reshape(want.shape), want)
 
+    # the way back: C -> B -> A must reproduce the layout-B and layout-A blocks
+    backB = [np.full(count, np.nan) for _ in range(world)]
+    backA = [np.full(count, np.nan) for _ in range(world)]
+    for r, pp in enumerate(plans):
+        blockC = bufC[r].reshape(batch, NZ, pp.nyl2 * pp.nxl)
+        a, i, b = np.meshgrid(np.arange(batch), np.arange(NZ), np.arange(pp.nyl2 * pp.nxl), indexing="ij")
+        q, off = scatter_dest(a, i, b, *pp.map_cb())
+        col = [z * py + pp.ry for z in range(pz)]
+        for dst in range(pz):
+            sel = q == dst
+            backB[col[dst]][off[sel]] = blockC[sel]
+    for r in range(world):
+        np.testing.assert_array_equal(backB[r], bufB[r])
+    for r, pp in enumerate(plans):
+        blockB = backB[r].reshape(batch * pp.nzl, NY, pp.nxl)
+        a, i, b = np.meshgrid(np.arange(batch * pp.nzl), np.arange(NY), np.arange(pp.nxl), indexing="ij")
+        q, off = scatter_dest(a, i, b, *pp.map_ba())
+        row = [pp.rz * py + y for y in range(py)]
+        for dst in range(py):
+            sel = q == dst
+            backA[row[dst]][off[sel]] = blockB[sel]
+    for r, pp in enumerate(plans):
+        want = G[:, pp.rz * pp.nzl:(pp.rz + 1) * pp.nzl, pp.ry * pp.nyl:(pp.ry + 1) * pp.nyl, :]
+        np.testing.assert_array_equal(backA[r].reshape(want.shape), want)
+
 
 def _run_workers(world, same_gpu):
     port = free_port()
