@@ -87,6 +87,11 @@ int pt_grid_axpoints(const double* grid_row, int64_t stride, int64_t n, double* 
  * image of the CGL set, either orientation).  D is n*n row-major.  Recursion of Welfert with
  * the negative-sum diagonal, sequential summation order (oracle/operators.py:cheb_mat). */
 int pt_gen_chebmat(const double* x, int n, int order, double* D, pt_stream_t stream);
+/* Flipping trick: overwrite the rows below the middle (and the right part of the middle row of an
+ * odd n) by the mirror image of the rows above, D[i][j] = sign * D[n-1-i][n-1-j] (sign = +1 / -1
+ * for even / odd derivative orders).  ChebMat applies it on CGL axes: the matrix is then exactly
+ * centro(anti)symmetric, which the even-odd kernels below exploit (oracle/operators.py:cheb_mat). */
+int pt_flip_symmetrize(double* D, int n, int sign, pt_stream_t stream);
 /* Polynomial collocation differentiation matrix on ARBITRARY distinct nodes (a non-affine
  * mapper of the reference, grid.py:201-207, returns nodes only): barycentric weights
  * w_j = 1/prod(x_j - x_k) held as mantissa*2^exponent, D1_ij = (w_j/w_i)/(x_i-x_j), higher
@@ -132,6 +137,24 @@ int pt_operator_pack(const double* D, int n_out, int n_in, int64_t ldD, double* 
 int pt_dense_apply(const double* packed, int n_out, int n_in, const double* U, double* Y,
                    int64_t after, int64_t before, double alpha, double beta,
                    const double* scale, int scale_mode, int64_t scale_len, pt_stream_t stream);
+
+/* ---- K1/K2 for centrosymmetric operators: even-odd decomposition (half the tensor-core work) ---- */
+/* Largest entrywise violation of J D J = sign * D (J = order reversal), relative to the entry:
+ * 0 for an exactly centro(anti)symmetric matrix.  Written to *worst_host (synchronises). */
+int pt_operator_symmetry(const double* D, int n, int sign, double* worst_host, pt_stream_t stream);
+/* Doubles of each of the two packed half operators. */
+int64_t pt_packed_eo_size(int n);
+/* Ae[i][k] = (D[i][k] + D[i][n-1-k])/2 and Ao[i][k] = (D[i][k] - D[i][n-1-k])/2 for i, k < ceil(n/2)
+ * in the fragment-major layout of the apply kernels (the middle column of an odd n holds D/2, 0). */
+int pt_operator_pack_eo(const double* D, int n, double* packed_even, double* packed_odd, pt_stream_t stream);
+/* Same contract as pt_dense_apply for an operator with J D J = sign * D: rows i < ceil(n/2) are
+ * computed as Ae (u + Ju) + Ao (u - Ju) (exact algebra), rows n-1-i follow from the symmetry.
+ * Two half-size products instead of one full-size product; E = u + Ju, O = u - Ju are formed in
+ * the kernel from two staged field tiles, no extra pass over the field. */
+int pt_dense_apply_eo(const double* packed_even, const double* packed_odd, int n, int sign,
+                      const double* U, double* Y, int64_t after, int64_t before, double alpha,
+                      double beta, const double* scale, int scale_mode, int64_t scale_len,
+                      pt_stream_t stream);
 
 /* ---- FourMat through the FFT ----------------------------------------- */
 /* tw[2*m], tw[2*m+1] = cos, -sin of 2 pi m / n for m < n (n complex doubles); n a power of two. */
@@ -240,6 +263,10 @@ typedef struct pt_scatter_map {
 int pt_dense_apply_scatter(const double* packed, int n_out, int n_in, const double* U,
                            const double* C, int64_t after, int64_t before, double alpha,
                            double beta, const pt_scatter_map* map, pt_stream_t stream);
+/* pt_dense_apply_scatter for a centrosymmetric operator (pt_dense_apply_eo). */
+int pt_dense_apply_eo_scatter(const double* packed_even, const double* packed_odd, int n, int sign,
+                              const double* U, const double* C, int64_t after, int64_t before,
+                              double alpha, double beta, const pt_scatter_map* map, pt_stream_t stream);
 /* The same redistribution for an array that is only moved (the field itself): 16-byte peer
  * stores, no staging buffer, no pack/unpack pass.  before == 1 requires s_i == 1. */
 int pt_peer_scatter(const double* src, int n, int64_t after, int64_t before,

@@ -73,9 +73,25 @@ def _seq_row_sum(M):
     return np.cumsum(M, axis=1)[:, -1]
 
 
-def cheb_mat(x, order=1):
+def flip_symmetrize(D, sign):
+    """Flipping trick (Don & Solomonoff 1995): rows below the middle, and the right part of the
+    middle row of an odd n, become the mirror image of the rows above, D[i,j] = sign*D[n-1-i,n-1-j]
+    (same rule as pt_flip_symmetrize)."""
+    n = D.shape[0]
+    D = D.copy()
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    mi, mj = n - 1 - i, n - 1 - j
+    sel = (i > mi) | ((i == mi) & (j > mj))
+    D[sel] = sign * D[mi[sel], mj[sel]]
+    if sign < 0 and n % 2 == 1:
+        D[n // 2, n // 2] = 0.0        # the centre of a centro-antisymmetric matrix is its own negative
+    return D
+
+
+def cheb_mat(x, order=1, flip=True):
     """Collocation differentiation matrix of ``order`` on nodes ``x`` (any affine image of the
-    CGL set, either orientation).
+    CGL set, either orientation).  With ``flip`` (default, what ChebMat generates) the lower half
+    is the mirror image of the upper half, so the matrix is exactly centro(anti)symmetric.
 
     D1_ij = (c_i/c_j)/(x_i-x_j), c_0 = c_{n-1} = 2 else 1, c_i <- c_i(-1)^i;
     D^(l)_ij = l/(x_i-x_j) * ((c_i/c_j) D^(l-1)_ii - D^(l-1)_ij);
@@ -97,7 +113,7 @@ def cheb_mat(x, order=1):
         Dn = np.where(off, (l / dx) * (cr * diag[:, None] - D), 0.0)
         Dn[~off] = -_seq_row_sum(Dn)
         D = Dn
-    return D
+    return flip_symmetrize(D, 1 if order % 2 == 0 else -1) if flip else D
 
 
 def bary_mat(x, order=1):
@@ -168,6 +184,8 @@ def four_col(n, period, order):
     if order == 1:
         v = ((s * 0.5) * sign) * (cs / sn) if even else ((s * 0.5) * sign) / sn
         col[k] = np.where(fold, -v, v)
+        if even:
+            col[n // 2] = 0.0          # cot(pi/2) = 0 exactly (the rounded pi/2 would leave 6e-17)
     else:
         s2 = s * s
         sn2 = sn * sn

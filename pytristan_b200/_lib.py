@@ -79,6 +79,14 @@ SIGNATURES = {
     "pt_operator_pack": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_i64, _c_ptr, _c_ptr]),
     "pt_dense_apply": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64,
                                 _c_f64, _c_ptr, _c_i32, _c_i64, _c_ptr]),
+    "pt_flip_symmetrize": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr]),
+    "pt_operator_symmetry": (_c_i32, [_c_ptr, _c_i32, _c_i32, ctypes.POINTER(_c_f64), _c_ptr]),
+    "pt_packed_eo_size": (_c_i64, [_c_i32]),
+    "pt_operator_pack_eo": (_c_i32, [_c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
+    "pt_dense_apply_eo": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64, _c_f64,
+                                   _c_ptr, _c_i32, _c_i64, _c_ptr]),
+    "pt_dense_apply_eo_scatter": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64,
+                                           _c_f64, ctypes.POINTER(ScatterMap), _c_ptr]),
     "pt_fourier_twiddles": (_c_i32, [_c_i32, _c_ptr, _c_ptr]),
     "pt_fourier_apply": (_c_i32, [_c_ptr, _c_i32, _c_f64, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64, _c_f64,
                                   _c_ptr, _c_i64, _c_ptr]),

@@ -1,0 +1,580 @@
+// K1/K2 for centrosymmetric operators — the even-odd decomposition on FP64 tensor cores.
+//
+// Fourier differentiation matrices, and Chebyshev collocation matrices on symmetric node sets,
+// satisfy J D J = s D with J the order reversal and s = (-1)^order.  Writing, for k < H = ceil(n/2),
+//     E[k] = u[k] + u[n-1-k],   O[k] = u[k] - u[n-1-k],
+//     Ae[i][k] = (D[i][k] + D[i][n-1-k]) / 2,   Ao[i][k] = (D[i][k] - D[i][n-1-k]) / 2
+// (column (n-1)/2 of Ae is D[i][k]/2 when n is odd: E doubles that element), the rows i < H are
+//     y[i] = sum_k Ae[i][k] E[k] + sum_k Ao[i][k] O[k] = ze[i] + zo[i]            (exact algebra)
+// and the symmetry gives the other half for free:   y[n-1-i] = s * (ze[i] - zo[i]).
+// Two H x H products replace one n x n product: HALF the tensor-core work for the same result
+// (Solomonoff 1992).  Everything is fused here: E and O are formed from the two staged field
+// tiles when the B fragments are read (one DADD + one DSUB per fragment), ze and zo accumulate in
+// the same thread, and the epilogue writes rows i and n-1-i — no extra pass over the field, no
+// extra HBM traffic.  Layout conventions, staging (cp.async ring, fragment-major operator panels,
+// pitch = 4 mod 16) and the fused alpha/beta/scale/scatter epilogue are those of dense_apply.cu.
+#include "dense_common.cuh"
+#include <string.h>
+
+using namespace ptdense;
+
+namespace {
+
+struct EoParams {
+  const double* __restrict__ Dpe;   // packed Ae: [KPH][MPH][4]
+  const double* __restrict__ Dpo;   // packed Ao
+  const double* __restrict__ U;
+  double* __restrict__ Y;
+  const double* __restrict__ C;     // beta input (== Y unless scattering)
+  const double* __restrict__ scale;
+  ScatterDev sc;
+  int n, H;                         // operator size, half size ceil(n/2)
+  int MPH, KPH;                     // padded half rows, k-panels of the half problem
+  int rt_per_block, m_blocks;       // row-tiles (8 half-rows) per CTA
+  int sign;                         // +1: J D J = D, -1: J D J = -D
+  int64_t before, NN, slab;         // slab = n*before
+  double alpha, beta;
+  int scale_mode;
+  int64_t scale_len;
+};
+
+// WARPS_M x WARPS_N warps; a warp owns up to WR row-tiles of the half problem (each with an even and
+// an odd accumulator set) x WN column tiles.
+template <int WARPS_M, int WARPS_N, int WR, int WN, int BKP, int STAGES, bool KCONTIG>
+struct EoCfg {
+  static constexpr int NT = WARPS_M * WARPS_N * 32;
+  static constexpr int BMH = WARPS_M * WR * 8;                      // half-rows per CTA
+  static constexpr int BN = WARPS_N * WN * 8;
+  static constexpr int BK = BKP * 4;
+  static constexpr int A_STAGE = BKP * 2 * BMH * 4;                 // per panel: [even rows][odd rows] x 4
+  static constexpr int PB = KCONTIG ? (BK + 4) : (BN + 4);
+  static constexpr int B_TILE = KCONTIG ? BN * PB : BK * PB;
+  static constexpr int STAGE = A_STAGE + 2 * B_TILE;                // field tile + mirrored field tile
+  static constexpr size_t SMEM = size_t(STAGES) * STAGE * sizeof(double);
+};
+
+template <class C, int RT, int WR, int WN, bool KCONTIG, bool VEC16>
+__device__ __forceinline__ void eo_frags(const double* As, const double* B1, const double* B2, int pp,
+                                         double (&ae)[WR], double (&ao)[WR], double (&be)[WN], double (&bo)[WN]) {
+#pragma unroll
+  for (int i = 0; i < RT; ++i) {
+    ae[i] = As[(pp * 2 * C::BMH + i * 8) * 4];
+    ao[i] = As[(pp * 2 * C::BMH + C::BMH + i * 8) * 4];
+  }
+  // mirrored tile: 16-byte copies keep the memory order inside a pair, i.e. the pair is swapped
+  // with respect to the mirrored k index
+#pragma unroll
+  for (int j = 0; j < WN; ++j) {
+    double f1, f2;
+    if (KCONTIG) {
+      f1 = B1[j * 8 * C::PB + pp * 4];
+      f2 = B2[j * 8 * C::PB + pp * 4];      // B2 already points at the (possibly pair-swapped) k slot
+    } else {
+      f1 = B1[pp * 4 * C::PB + j * 8];
+      f2 = B2[pp * 4 * C::PB + j * 8];
+    }
+    be[j] = __dadd_rn(f1, f2);
+    bo[j] = __dsub_rn(f1, f2);
+  }
+}
+
+template <class C, int RT, int WR, int WN, int BKP, bool KCONTIG, bool VEC16>
+__device__ __forceinline__ void eo_compute(const double* As, const double* B1, const double* B2, int npanels,
+                                           double (&acce)[WR][WN][2], double (&acco)[WR][WN][2]) {
+  if (npanels == BKP) {
+    double ae[2][WR], ao[2][WR], be[2][WN], bo[2][WN];
+    eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, 0, ae[0], ao[0], be[0], bo[0]);
+#pragma unroll
+    for (int pp = 0; pp < BKP; ++pp) {
+      if (pp + 1 < BKP)
+        eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pp + 1, ae[(pp + 1) & 1], ao[(pp + 1) & 1],
+                                                 be[(pp + 1) & 1], bo[(pp + 1) & 1]);
+#pragma unroll
+      for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int j = 0; j < WN; ++j) {
+          dmma(acce[i][j][0], acce[i][j][1], ae[pp & 1][i], be[pp & 1][j]);
+          dmma(acco[i][j][0], acco[i][j][1], ao[pp & 1][i], bo[pp & 1][j]);
+        }
+    }
+  } else {
+#pragma unroll 1
+    for (int pp = 0; pp < npanels; ++pp) {
+      double ae[WR], ao[WR], be[WN], bo[WN];
+      eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pp, ae, ao, be, bo);
+#pragma unroll
+      for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int j = 0; j < WN; ++j) {
+          dmma(acce[i][j][0], acce[i][j][1], ae[i], be[j]);
+          dmma(acco[i][j][0], acco[i][j][1], ao[i], bo[j]);
+        }
+    }
+  }
+}
+
+// exact row-tile dispatch (predicated-off DMMAs still occupy the tensor pipe)
+template <class C, int RT, int WR, int WN, int BKP, bool KCONTIG, bool VEC16>
+struct EoDispatch {
+  static __device__ __forceinline__ void run(int my_rt, const double* As, const double* B1, const double* B2,
+                                             int npanels, double (&acce)[WR][WN][2], double (&acco)[WR][WN][2]) {
+    if (my_rt == RT) eo_compute<C, RT, WR, WN, BKP, KCONTIG, VEC16>(As, B1, B2, npanels, acce, acco);
+    else EoDispatch<C, RT - 1, WR, WN, BKP, KCONTIG, VEC16>::run(my_rt, As, B1, B2, npanels, acce, acco);
+  }
+};
+template <class C, int WR, int WN, int BKP, bool KCONTIG, bool VEC16>
+struct EoDispatch<C, 0, WR, WN, BKP, KCONTIG, VEC16> {
+  static __device__ __forceinline__ void run(int, const double*, const double*, const double*, int,
+                                             double (&)[WR][WN][2], double (&)[WR][WN][2]) {}
+};
+
+template <int WARPS_M, int WARPS_N, int WR, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB, bool SCAT>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_kernel(const EoParams p) {
+  using C = EoCfg<WARPS_M, WARPS_N, WR, WN, BKP, STAGES, KCONTIG>;
+  extern __shared__ __align__(128) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wn = warp % WARPS_N, wm = warp / WARPS_N;
+  const int g = lane >> 2, t = lane & 3;
+
+  const int m_block = blockIdx.x % p.m_blocks;
+  const int64_t n_block = blockIdx.x / p.m_blocks;
+  const int rtiles_total = p.MPH >> 3;
+  const int rt0 = m_block * p.rt_per_block;
+  const int rt_count = min(p.rt_per_block, rtiles_total - rt0);
+  const int m0h = rt0 * 8;                      // first half-row of the CTA
+  const int rows_blk = rt_count * 8;
+  const int64_t n0 = n_block * C::BN;
+  const int q = (rt_count + WARPS_M - 1) / WARPS_M;
+  const int my_rt0 = wm * q;
+  const int my_rt = max(0, min(q, rt_count - my_rt0));
+  const int nchunks = (p.KPH + BKP - 1) / BKP;
+  const int n = p.n;
+
+  constexpr int EPC = VEC16 ? 2 : 1;
+  constexpr int CPR1 = C::BN / EPC, RPP1 = C::NT / CPR1;            // K1: chunks per k-row, k-rows per pass
+  constexpr int CPR2 = C::BK / EPC, RPP2 = C::NT / CPR2;            // K2: chunks per column, columns per pass
+  static_assert(KCONTIG || (C::NT % CPR1 == 0 && C::BK % RPP1 == 0), "K1 loader shape");
+  static_assert(!KCONTIG || (C::NT % CPR2 == 0 && C::BN % RPP2 == 0), "K2 loader shape");
+  constexpr int APIECES = C::BMH * 2;                                // 16-byte pieces of one panel half
+  constexpr int ASUB = (APIECES + C::NT - 1) / C::NT;
+
+  // ---- loader: per-thread constants -----------------------------------------------------------------
+  const int b_cc = KCONTIG ? tid % CPR2 : tid % CPR1;
+  const int b_r0 = KCONTIG ? tid / CPR2 : tid / CPR1;
+  const double* b_base = p.U;                   // K1: address of (a, k = 0, b) of this thread's column chunk
+  bool b_col_ok = false;
+  if (!KCONTIG) {
+    const int64_t nn = n0 + int64_t(b_cc) * EPC;
+    b_col_ok = nn < p.NN;
+    if (b_col_ok) {
+      const int64_t a = nn / p.before;
+      b_base = p.U + a * p.slab + (nn - a * p.before);
+    }
+  }
+
+  // generic (bounds-checked) loader: the chunk that crosses the end of the k range, tiny operators
+  auto load_stage_edge = [&](int stage, int chunk) {
+    double* As = smem + size_t(stage) * C::STAGE;
+    double* B1 = As + C::A_STAGE;
+    double* B2 = B1 + C::B_TILE;
+    const int kp0 = chunk * BKP;
+    // operator panels: [pp][even rows | odd rows]
+#pragma unroll
+    for (int pp = 0; pp < BKP; ++pp)
+#pragma unroll
+      for (int sub = 0; sub < ASUB; ++sub) {
+        const int c = tid + sub * C::NT;
+        if (APIECES % C::NT == 0 || c < APIECES) {
+          const bool ok = (kp0 + pp < p.KPH) && ((c >> 1) < rows_blk);
+          const size_t off = (size_t(kp0 + pp) * p.MPH + m0h) * 4 + c * 2;
+          cp_async16(As + (pp * 2 * C::BMH) * 4 + c * 2, ok ? p.Dpe + off : p.Dpe, ok ? 16 : 0);
+          cp_async16(As + (pp * 2 * C::BMH + C::BMH) * 4 + c * 2, ok ? p.Dpo + off : p.Dpo, ok ? 16 : 0);
+        }
+      }
+    // field tiles: rows k (tile 1) and n-1-k (tile 2) for the 16 values of k of this chunk
+    const int k0 = kp0 * 4;
+    if (!KCONTIG) {
+#pragma unroll
+      for (int r = 0; r < C::BK / RPP1; ++r) {
+        const int kr = b_r0 + r * RPP1;
+        const int k = k0 + kr;
+        const bool ok = b_col_ok && (k < n);
+        const double* s1 = ok ? b_base + int64_t(k) * p.before : p.U;
+        const double* s2 = ok ? b_base + int64_t(n - 1 - k) * p.before : p.U;
+        double* d1 = B1 + kr * C::PB + b_cc * EPC;
+        double* d2 = B2 + kr * C::PB + b_cc * EPC;
+        if (VEC16) { cp_async16(d1, s1, ok ? 16 : 0); cp_async16(d2, s2, ok ? 16 : 0); }
+        else { cp_async8(d1, s1, ok ? 8 : 0); cp_async8(d2, s2, ok ? 8 : 0); }
+      }
+    } else {
+      const int k = k0 + b_cc * EPC;            // first k of this thread's piece
+#pragma unroll
+      for (int r = 0; r < C::BN / RPP2; ++r) {
+        const int col = b_r0 + r * RPP2;
+        const int64_t nn = n0 + col;
+        // the piece k .. k+EPC-1 and its mirror n-EPC-k .. n-1-k lie inside the row iff k+EPC <= n
+        const bool ok = (nn < p.NN) && (k + EPC <= n);
+        const double* row = p.U + nn * n;
+        double* d1 = B1 + col * C::PB + b_cc * EPC;
+        double* d2 = B2 + col * C::PB + b_cc * EPC;
+        if (VEC16) {
+          cp_async16(d1, ok ? row + k : p.U, ok ? 16 : 0);
+          cp_async16(d2, ok ? row + (n - 2 - k) : p.U, ok ? 16 : 0);
+        } else {
+          cp_async8(d1, ok ? row + k : p.U, ok ? 8 : 0);
+          cp_async8(d2, ok ? row + (n - 1 - k) : p.U, ok ? 8 : 0);
+        }
+      }
+    }
+  };
+
+  // fast loader for chunks whose panels are all valid: running pointers, no index arithmetic in
+  // the loop (chunks are loaded in increasing order) — the loader burst is what keeps a warp away
+  // from the tensor pipe
+  const int64_t a_panel = int64_t(p.MPH) * 4;
+  const double* ae_ptr = p.Dpe + size_t(m0h) * 4 + tid * 2;
+  const double* ao_ptr = p.Dpo + size_t(m0h) * 4 + tid * 2;
+  unsigned a_ok = 0, a_in = 0;
+#pragma unroll
+  for (int sub = 0; sub < ASUB; ++sub) {
+    if (((tid + sub * C::NT) >> 1) < rows_blk) a_ok |= 1u << sub;
+    if (tid + sub * C::NT < APIECES) a_in |= 1u << sub;
+  }
+  const double *b1_ptr, *b2_ptr;
+  int64_t b_rstep, b_cstep;
+  unsigned b_ok = 0;
+  if (!KCONTIG) {
+    b1_ptr = b_base + int64_t(b_r0) * p.before;
+    b2_ptr = b_base + int64_t(n - 1 - b_r0) * p.before;
+    b_rstep = int64_t(RPP1) * p.before;            // tile 2 walks the rows downwards
+    b_cstep = int64_t(C::BK) * p.before;
+    b_ok = b_col_ok ? ~0u : 0u;
+  } else {
+    b1_ptr = p.U + (n0 + b_r0) * n + b_cc * EPC;
+    b2_ptr = p.U + (n0 + b_r0) * n + (n - EPC - b_cc * EPC);
+    b_rstep = int64_t(RPP2) * n;                   // next column: both tiles move the same way
+    b_cstep = C::BK;
+#pragma unroll
+    for (int r = 0; r < C::BN / RPP2; ++r)
+      if (n0 + b_r0 + r * RPP2 < p.NN) b_ok |= 1u << r;
+  }
+  const int fast_chunks = min(p.KPH / BKP, n / C::BK);   // all panels valid and all k + EPC <= n
+
+  auto load_stage = [&](int stage, int chunk) {
+    if (chunk >= fast_chunks) { load_stage_edge(stage, chunk); return; }
+    double* As = smem + size_t(stage) * C::STAGE;
+    double* B1 = As + C::A_STAGE;
+    double* B2 = B1 + C::B_TILE;
+#pragma unroll
+    for (int pp = 0; pp < BKP; ++pp)
+#pragma unroll
+      for (int sub = 0; sub < ASUB; ++sub) {
+        const bool ok = (a_ok >> sub) & 1u;
+        if (APIECES % C::NT == 0 || ((a_in >> sub) & 1u)) {
+          const int c2 = (tid + sub * C::NT) * 2;
+          cp_async16(As + (pp * 2 * C::BMH) * 4 + c2, ok ? ae_ptr + pp * a_panel + sub * C::NT * 2 : p.Dpe, ok ? 16 : 0);
+          cp_async16(As + (pp * 2 * C::BMH + C::BMH) * 4 + c2, ok ? ao_ptr + pp * a_panel + sub * C::NT * 2 : p.Dpo, ok ? 16 : 0);
+        }
+      }
+    ae_ptr += BKP * a_panel;
+    ao_ptr += BKP * a_panel;
+    constexpr int BR = KCONTIG ? C::BN / RPP2 : C::BK / RPP1;
+    constexpr int RPP = KCONTIG ? RPP2 : RPP1;
+#pragma unroll
+    for (int r = 0; r < BR; ++r) {
+      const bool ok = (b_ok >> (KCONTIG ? r : 0)) & 1u;
+      const int so = (b_r0 + r * RPP) * C::PB + b_cc * EPC;
+      const double* s1 = ok ? b1_ptr + r * b_rstep : p.U;
+      const double* s2 = ok ? (KCONTIG ? b2_ptr + r * b_rstep : b2_ptr - r * b_rstep) : p.U;
+      if (VEC16) { cp_async16(B1 + so, s1, ok ? 16 : 0); cp_async16(B2 + so, s2, ok ? 16 : 0); }
+      else { cp_async8(B1 + so, s1, ok ? 8 : 0); cp_async8(B2 + so, s2, ok ? 8 : 0); }
+    }
+    b1_ptr += b_cstep;
+    b2_ptr -= b_cstep;
+  };
+
+  double acce[WR][WN][2], acco[WR][WN][2];
+#pragma unroll
+  for (int i = 0; i < WR; ++i)
+#pragma unroll
+    for (int j = 0; j < WN; ++j) { acce[i][j][0] = acce[i][j][1] = 0.0; acco[i][j][0] = acco[i][j][1] = 0.0; }
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nchunks) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  const int a_off = my_rt0 * 32 + lane;
+  // B fragment: k = t, column = g.  In the mirrored tile of the contiguous-axis kernel a 16-byte
+  // piece holds (u[n-2-k], u[n-1-k]): the slot of mirrored index k is k ^ 1.
+  const int b1_off = KCONTIG ? ((wn * WN * 8 + g) * C::PB + t) : (t * C::PB + wn * WN * 8 + g);
+  const int b2_off = KCONTIG ? ((wn * WN * 8 + g) * C::PB + (VEC16 ? (t ^ 1) : t)) : b1_off;
+  const int nfull = p.KPH / BKP;
+  const int tail = p.KPH - nfull * BKP;
+
+  for (int kc = 0; kc < nchunks; ++kc) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = kc + STAGES - 1;
+      if (nxt < nchunks) load_stage(nxt % STAGES, nxt);
+      cp_async_commit();
+    }
+    const double* As = smem + size_t(kc % STAGES) * C::STAGE;
+    const double* B1 = As + C::A_STAGE;
+    const double* B2 = B1 + C::B_TILE;
+    EoDispatch<C, WR, WR, WN, BKP, KCONTIG, VEC16>::run(my_rt, As + a_off, B1 + b1_off, B2 + b2_off,
+                                                        kc < nfull ? BKP : tail, acce, acco);
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue: rows i (ze + zo) and n-1-i (s*(ze - zo)) ----------------------------------------------
+  const bool use_beta = (p.beta != 0.0);
+  const double sgn = double(p.sign);
+#pragma unroll
+  for (int j = 0; j < WN; ++j) {
+    const int64_t nn = n0 + (wn * WN + j) * 8 + 2 * t;
+    if (nn >= p.NN) continue;
+    const bool two = (nn + 1 < p.NN);
+    int64_t a0, b0, a1, b1;
+    if (KCONTIG) {
+      a0 = nn; b0 = 0; a1 = nn + 1; b1 = 0;
+    } else {
+      a0 = nn / p.before; b0 = nn - a0 * p.before;
+      if (b0 + 1 < p.before) { a1 = a0; b1 = b0 + 1; } else { a1 = a0 + 1; b1 = 0; }
+    }
+    double s0 = p.alpha, s1 = p.alpha;
+    if (p.scale_mode == PT_SCALE_AFTER) {
+      s0 *= p.scale[a0 % p.scale_len];
+      if (two) s1 *= p.scale[a1 % p.scale_len];
+    } else if (p.scale_mode == PT_SCALE_BEFORE) {
+      s0 *= p.scale[b0];
+      if (two) s1 *= p.scale[b1];
+    }
+    const int64_t l0 = a0 * p.slab + b0, l1 = a1 * p.slab + b1;
+    int64_t d0 = 0, d1 = 0;
+    if (SCAT) {
+      const int64_t q0 = a0 / p.sc.a_inner, q1 = a1 / p.sc.a_inner;
+      d0 = p.sc.offset + q0 * p.sc.s_outer + (a0 - q0 * p.sc.a_inner) * p.sc.s_inner + b0;
+      d1 = p.sc.offset + q1 * p.sc.s_outer + (a1 - q1 * p.sc.a_inner) * p.sc.s_inner + b1;
+    }
+#pragma unroll
+    for (int i = 0; i < WR; ++i) {
+      if (i >= my_rt) continue;
+      const int hrow = m0h + (my_rt0 + i) * 8 + g;
+      if (hrow >= p.H) continue;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int row = half == 0 ? hrow : n - 1 - hrow;
+        if (half == 1 && row == hrow) continue;          // middle row of an odd n: written once
+        double w0, w1;
+        if (half == 0) { w0 = __dadd_rn(acce[i][j][0], acco[i][j][0]); w1 = __dadd_rn(acce[i][j][1], acco[i][j][1]); }
+        else { w0 = __dmul_rn(sgn, __dsub_rn(acce[i][j][0], acco[i][j][0])); w1 = __dmul_rn(sgn, __dsub_rn(acce[i][j][1], acco[i][j][1])); }
+        double r0 = s0, r1 = s1;
+        if (p.scale_mode == PT_SCALE_ROW) { const double sr = p.scale[row]; r0 *= sr; r1 *= sr; }
+        double v0 = __dmul_rn(r0, w0), v1 = __dmul_rn(r1, w1);
+        const int64_t off = int64_t(row) * p.before;
+        const double* c0 = (SCAT ? p.C : p.Y) + l0 + off;
+        const double* c1 = (SCAT ? p.C : p.Y) + l1 + off;
+        double *y0, *y1;
+        if (SCAT) {
+          const int dq = row / p.sc.chunk;
+          double* db = p.sc.base[dq] + int64_t(row - dq * p.sc.chunk) * p.sc.s_i;
+          y0 = db + d0; y1 = db + d1;
+        } else {
+          y0 = p.Y + l0 + off; y1 = p.Y + l1 + off;
+        }
+        if (!KCONTIG && VEC16) {
+          if (use_beta) { const double2 o = *reinterpret_cast<const double2*>(c0); v0 = __fma_rn(p.beta, o.x, v0); v1 = __fma_rn(p.beta, o.y, v1); }
+          *reinterpret_cast<double2*>(y0) = make_double2(v0, v1);
+        } else {
+          if (use_beta) v0 = __fma_rn(p.beta, *c0, v0);
+          *y0 = v0;
+          if (two) {
+            if (use_beta) v1 = __fma_rn(p.beta, *c1, v1);
+            *y1 = v1;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Ae / Ao of a centrosymmetric operator in the fragment-major layout of the apply kernel
+__global__ void pack_eo_kernel(const double* __restrict__ D, int n, int H, int MPH, int KPH,
+                               double* __restrict__ pe, double* __restrict__ po) {
+  const int64_t total = int64_t(KPH) * MPH * 4;
+  const int mid = (n & 1) ? (n - 1) / 2 : -1;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int kk = int(idx & 3);
+    const int64_t r = idx >> 2;
+    const int i = int(r % MPH), k = int(r / MPH) * 4 + kk;
+    double ve = 0.0, vo = 0.0;
+    if (i < H && k < H) {
+      const double a = D[int64_t(i) * n + k], b = D[int64_t(i) * n + (n - 1 - k)];
+      if (k == mid) { ve = __dmul_rn(0.5, a); vo = 0.0; }      // E[mid] = 2 u[mid], O[mid] = 0
+      else { ve = __dmul_rn(0.5, __dadd_rn(a, b)); vo = __dmul_rn(0.5, __dsub_rn(a, b)); }
+    }
+    pe[idx] = ve;
+    po[idx] = vo;
+  }
+}
+
+// largest entrywise violation of J D J = s D, relative to the entry (atomicMax on the bit pattern of
+// a non-negative double)
+__global__ void symmetry_kernel(const double* __restrict__ D, int n, int sign, unsigned long long* worst) {
+  const int64_t total = int64_t(n) * n;
+  double w = 0.0;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int i = int(idx / n), j = int(idx % n);
+    const double a = D[idx], b = double(sign) * D[int64_t(n - 1 - i) * n + (n - 1 - j)];
+    const double d = fabs(a - b), m = fmax(fabs(a), fabs(b));
+    if (d > 0.0) w = fmax(w, d / m);
+  }
+  atomicMax(worst, (unsigned long long)__double_as_longlong(w));
+}
+
+inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
+
+template <int WARPS_M, int WARPS_N, int WR, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB, bool SCAT>
+int launch_eo(EoParams& p, cudaStream_t stream) {
+  using C = EoCfg<WARPS_M, WARPS_N, WR, WN, BKP, STAGES, KCONTIG>;
+  auto kern = dense_apply_eo_kernel<WARPS_M, WARPS_N, WR, WN, BKP, STAGES, KCONTIG, VEC16, MINB, SCAT>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  PT_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
+    attr_set[dev] = true;
+  }
+  const int rtiles = p.MPH / 8;
+  const int max_rt = WARPS_M * WR;
+  p.m_blocks = (rtiles + max_rt - 1) / max_rt;
+  p.rt_per_block = (rtiles + p.m_blocks - 1) / p.m_blocks;
+  p.m_blocks = (rtiles + p.rt_per_block - 1) / p.rt_per_block;
+  const int64_t n_blocks = (p.NN + C::BN - 1) / C::BN;
+  const int64_t grid = n_blocks * p.m_blocks;
+  if (grid <= 0) return PT_OK;
+  if (grid > 2147483647LL) return pt::fail(PT_ERR_UNSUPPORTED, "pt_dense_apply_eo: grid too large");
+  kern<<<unsigned(grid), C::NT, C::SMEM, stream>>>(p);
+  return pt::check_launch("pt_dense_apply_eo");
+}
+
+int g_eo_config = -1;   // tuning hook (pt_debug_set_eo_config); -1 = choose by shape
+
+template <bool KCONTIG, bool VEC16, bool SCAT>
+int launch_eo_shape(EoParams& p, cudaStream_t stream) {
+  // CTAs of the large tile; below one per SM the small tile fills the GPU better
+  const int64_t ctas = ((p.H + 63) / 64) * ((p.NN + 63) / 64);
+  const int cfg = g_eo_config >= 0 ? g_eo_config : (ctas < pt::sm_count() ? 1 : 0);
+  if (cfg == 1) return launch_eo<2, 2, 2, 2, 4, 3, KCONTIG, VEC16, 4, SCAT>(p, stream);   // 32 half-rows x 32 columns
+  return launch_eo<2, 2, 4, 4, 4, 3, KCONTIG, VEC16, 2, SCAT>(p, stream);                 // 64 half-rows x 64 columns
+}
+
+int apply_eo_impl(const double* pe, const double* po, int n, int sign, const double* U, double* Y, const double* C,
+                  int64_t after, int64_t before, double alpha, double beta, const double* scale, int scale_mode,
+                  int64_t scale_len, const pt_scatter_map* map, pt_stream_t stream) {
+  PT_REQUIRE(pe && po && U, "pt_dense_apply_eo: null pointer");
+  PT_REQUIRE(n >= 2, "pt_dense_apply_eo: n=%d", n);
+  PT_REQUIRE(sign == 1 || sign == -1, "pt_dense_apply_eo: sign must be +1 or -1");
+  PT_REQUIRE(after >= 0 && before >= 1, "pt_dense_apply_eo: bad field shape");
+  PT_REQUIRE(scale_mode >= PT_SCALE_NONE && scale_mode <= PT_SCALE_BEFORE, "pt_dense_apply_eo: bad scale_mode %d", scale_mode);
+  PT_REQUIRE(scale_mode == PT_SCALE_NONE || scale != nullptr, "pt_dense_apply_eo: scale is null");
+  PT_REQUIRE(scale_mode != PT_SCALE_AFTER || scale_len > 0, "pt_dense_apply_eo: scale_len must be > 0");
+  if (after == 0) return PT_OK;
+  EoParams p;
+  p.Dpe = pe; p.Dpo = po; p.U = U; p.Y = Y; p.C = C; p.scale = scale;
+  p.sc = map ? ScatterDev{map->base, map->chunk, map->a_inner, map->s_outer, map->s_inner, map->s_i, map->offset}
+             : ScatterDev{nullptr, 1, 1, 0, 0, 0, 0};
+  p.n = n; p.H = (n + 1) / 2;
+  p.MPH = 8 * ((p.H + 7) / 8);
+  p.KPH = (p.H + 3) / 4;
+  p.sign = sign;
+  p.before = before; p.NN = after * before; p.slab = int64_t(n) * before;
+  p.alpha = alpha; p.beta = beta; p.scale_mode = scale_mode; p.scale_len = scale_len > 0 ? scale_len : 1;
+  p.m_blocks = 1; p.rt_per_block = 1;
+  cudaStream_t st = pt::as_stream(stream);
+  if (before == 1) {
+    const bool vec = (n % 2 == 0) && aligned16(U);
+    if (map) return vec ? launch_eo_shape<true, true, true>(p, st) : launch_eo_shape<true, false, true>(p, st);
+    return vec ? launch_eo_shape<true, true, false>(p, st) : launch_eo_shape<true, false, false>(p, st);
+  }
+  if (map) {
+    const bool even = !((map->s_outer | map->s_inner | map->s_i | map->offset) & 1);
+    const bool vec = (before % 2 == 0) && aligned16(U) && (C == nullptr || aligned16(C)) && even;
+    return vec ? launch_eo_shape<false, true, true>(p, st) : launch_eo_shape<false, false, true>(p, st);
+  }
+  const bool vec = (before % 2 == 0) && aligned16(U) && aligned16(Y);
+  return vec ? launch_eo_shape<false, true, false>(p, st) : launch_eo_shape<false, false, false>(p, st);
+}
+
+}  // namespace
+
+extern "C" int pt_debug_set_eo_config(int id) {
+  g_eo_config = id;
+  return PT_OK;
+}
+
+extern "C" int64_t pt_packed_eo_size(int n) {
+  if (n <= 0) return 0;
+  const int64_t H = (int64_t(n) + 1) / 2;
+  return ((H + 3) / 4) * (8 * ((H + 7) / 8)) * 4;
+}
+
+extern "C" int pt_operator_symmetry(const double* D, int n, int sign, double* worst_host, pt_stream_t stream) {
+  PT_REQUIRE(D && worst_host, "pt_operator_symmetry: null pointer");
+  PT_REQUIRE(n >= 1 && (sign == 1 || sign == -1), "pt_operator_symmetry: bad argument");
+  cudaStream_t st = pt::as_stream(stream);
+  unsigned long long* d_w = nullptr;
+  PT_CUDA(cudaMalloc(&d_w, sizeof(unsigned long long)));
+  PT_CUDA(cudaMemsetAsync(d_w, 0, sizeof(unsigned long long), st));
+  int64_t blocks = (int64_t(n) * n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  symmetry_kernel<<<unsigned(blocks), 256, 0, st>>>(D, n, sign, d_w);
+  unsigned long long bits = 0;
+  cudaError_t e = cudaMemcpyAsync(&bits, d_w, sizeof(bits), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_w);
+  if (e != cudaSuccess) return pt::fail(PT_ERR_CUDA, "pt_operator_symmetry: %s", cudaGetErrorString(e));
+  double w;
+  memcpy(&w, &bits, sizeof(w));
+  *worst_host = w;
+  return PT_OK;
+}
+
+extern "C" int pt_operator_pack_eo(const double* D, int n, double* packed_even, double* packed_odd,
+                                   pt_stream_t stream) {
+  PT_REQUIRE(D && packed_even && packed_odd, "pt_operator_pack_eo: null pointer");
+  PT_REQUIRE(n >= 2, "pt_operator_pack_eo: n=%d", n);
+  const int H = (n + 1) / 2, MPH = 8 * ((H + 7) / 8), KPH = (H + 3) / 4;
+  const int64_t total = int64_t(KPH) * MPH * 4;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_eo_kernel<<<unsigned(blocks), 256, 0, pt::as_stream(stream)>>>(D, n, H, MPH, KPH, packed_even, packed_odd);
+  return pt::check_launch("pt_operator_pack_eo");
+}
+
+extern "C" int pt_dense_apply_eo(const double* packed_even, const double* packed_odd, int n, int sign,
+                                 const double* U, double* Y, int64_t after, int64_t before, double alpha,
+                                 double beta, const double* scale, int scale_mode, int64_t scale_len,
+                                 pt_stream_t stream) {
+  PT_REQUIRE(Y != nullptr, "pt_dense_apply_eo: null pointer");
+  PT_REQUIRE(U != Y, "pt_dense_apply_eo: in-place application is not supported");
+  return apply_eo_impl(packed_even, packed_odd, n, sign, U, Y, Y, after, before, alpha, beta, scale, scale_mode,
+                       scale_len, nullptr, stream);
+}
+
+extern "C" int pt_dense_apply_eo_scatter(const double* packed_even, const double* packed_odd, int n, int sign,
+                                         const double* U, const double* C, int64_t after, int64_t before,
+                                         double alpha, double beta, const pt_scatter_map* map, pt_stream_t stream) {
+  PT_REQUIRE(map && map->base, "pt_dense_apply_eo_scatter: null map");
+  PT_REQUIRE(map->nranks >= 1 && map->chunk >= 1 && int64_t(map->chunk) * map->nranks >= n,
+             "pt_dense_apply_eo_scatter: %d destinations x %d rows do not cover n=%d", map->nranks, map->chunk, n);
+  PT_REQUIRE(map->a_inner >= 1, "pt_dense_apply_eo_scatter: a_inner must be >= 1");
+  PT_REQUIRE(beta == 0.0 || C != nullptr, "pt_dense_apply_eo_scatter: beta != 0 needs C");
+  return apply_eo_impl(packed_even, packed_odd, n, sign, U, nullptr, C ? C : U, after, before, alpha, beta, nullptr,
+                       PT_SCALE_NONE, 0, map, stream);
+}

@@ -128,6 +128,18 @@ __global__ void cheb_diag_kernel(int n, double* D) {
   D[int64_t(i) * n + i] = -s;
 }
 
+// flipping trick (Don & Solomonoff 1995): rows below the middle (and the right part of the middle
+// row of an odd n) are the mirror image of the rows above it, D[i][j] = s * D[n-1-i][n-1-j]:
+// the matrix is exactly centrosymmetric (s = +1) / centro-antisymmetric (s = -1)
+__global__ void flip_kernel(double* D, int n, int sign) {
+  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (idx >= int64_t(n) * n) return;
+  const int i = int(idx / n), j = int(idx % n);
+  const int mi = n - 1 - i, mj = n - 1 - j;
+  if (i > mi || (i == mi && j > mj)) D[idx] = __dmul_rn(double(sign), D[int64_t(mi) * n + mj]);
+  else if (sign < 0 && i == mi && j == mj) D[idx] = 0.0;   // the centre is its own negative
+}
+
 // ---- K6: Fourier ---------------------------------------------------------------------------------
 __device__ double four_col(int k, int n, double s, int order) {
   // entry for (i - j) mod n == k; k > n/2 folded by symmetry (order 1 odd, order 2 even)
@@ -138,6 +150,9 @@ __device__ double four_col(int k, int n, double s, int order) {
     if ((n & 1) == 0) return -__dmul_rn(s2, __dadd_rn(__ddiv_rn(nn, 12.0), 1.0 / 6.0));
     return -__dmul_rn(s2, __ddiv_rn(__dsub_rn(nn, 1.0), 12.0));
   }
+  // antipodal node of an even n, odd order: cot(pi/2) is exactly 0 (the rounded pi/2 would leave
+  // 6e-17); it also makes the matrix exactly centro-antisymmetric (dense_apply_eo.cu)
+  if (order == 1 && 2 * k == n) return 0.0;
   const bool fold = 2 * k > n;
   const int kk = fold ? n - k : k;
   const double theta = __ddiv_rn(__dmul_rn(double(kk), kPi), double(n));
@@ -515,6 +530,13 @@ extern "C" int pt_gen_chebmat(const double* x, int n, int order, double* D, pt_s
   return pt::check_launch("pt_gen_chebmat");
 }
 
+
+extern "C" int pt_flip_symmetrize(double* D, int n, int sign, pt_stream_t stream) {
+  PT_REQUIRE(D, "pt_flip_symmetrize: null pointer");
+  PT_REQUIRE(n >= 1 && (sign == 1 || sign == -1), "pt_flip_symmetrize: bad argument");
+  flip_kernel<<<blocks_for(int64_t(n) * n, 256), 256, 0, pt::as_stream(stream)>>>(D, n, sign);
+  return pt::check_launch("pt_flip_symmetrize");
+}
 
 extern "C" int pt_gen_barymat(const double* x, int n, int order, double* D, double* work,
                               pt_stream_t stream) {

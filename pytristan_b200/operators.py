@@ -114,6 +114,13 @@ def _field_to_device(u):
     return torch.from_numpy(a).cuda(), "numpy"
 
 
+# Even-odd application of centrosymmetric operators (csrc/dense_apply_eo.cu): operators whose
+# entries satisfy J D J = +-D to within EO_TOLERANCE (entrywise, relative) are applied as two
+# half-size tensor-core products.  Set EVEN_ODD = False to force the plain kernel.
+EVEN_ODD = True
+EO_TOLERANCE = 4.0e-15
+
+
 class _DiffMat(np.ndarray):
     """Common machinery: attributes, device copies, application, lifting."""
 
@@ -132,6 +139,7 @@ class _DiffMat(np.ndarray):
         self._dev = None
         self._packed = None
         self._band = None
+        self._eo = None
 
     # -- construction helpers ------------------------------------------------------------------
     @classmethod
@@ -143,6 +151,7 @@ class _DiffMat(np.ndarray):
         obj._dev = d_mat
         obj._packed = None
         obj._band = None
+        obj._eo = None
         return obj
 
     @property
@@ -169,6 +178,30 @@ class _DiffMat(np.ndarray):
             )
             self._packed = packed
         return self._packed
+
+    def _eo_forms(self):
+        """``(sign, packed_even, packed_odd)`` when the operator is centro(anti)symmetric to within
+        EO_TOLERANCE (decided once, on the device), else None."""
+        if getattr(self, "_eo", None) is None:
+            self._eo = False
+            n = int(self.shape[0])
+            if self.ndim == 2 and self.shape[0] == self.shape[1] and n >= 16:
+                lib = _lib.load()
+                d = self.device()
+                order = getattr(self, "order", None)
+                signs = (1, -1) if order is None else ((1,) if order % 2 == 0 else (-1,))
+                for sign in signs:
+                    worst = ctypes.c_double(0.0)
+                    _lib.check(lib.pt_operator_symmetry(_lib.dptr(d), n, sign, ctypes.byref(worst),
+                                                        _lib.stream_ptr()), "pt_operator_symmetry")
+                    if worst.value <= EO_TOLERANCE:
+                        size = lib.pt_packed_eo_size(n)
+                        pe, po = _lib.empty((size,)), _lib.empty((size,))
+                        _lib.check(lib.pt_operator_pack_eo(_lib.dptr(d), n, _lib.dptr(pe), _lib.dptr(po),
+                                                           _lib.stream_ptr()), "pt_operator_pack_eo")
+                        self._eo = (sign, pe, po)
+                        break
+        return self._eo or None
 
     # -- geometry -----------------------------------------------------------------------------------
     def _split(self, size, npts=None, axis=None):
@@ -227,6 +260,15 @@ class _DiffMat(np.ndarray):
             need = {"row": n, "after": 1, "before": before}[scale_mode]
             if slen < need:
                 raise ValueError("scale vector is too short")
+        eo = self._eo_forms() if EVEN_ODD else None
+        if eo is not None:
+            _lib.check(
+                lib.pt_dense_apply_eo(_lib.dptr(eo[1]), _lib.dptr(eo[2]), n, eo[0], _lib.dptr(d_u), _lib.dptr(d_y),
+                                      after, before, float(alpha), float(beta), _lib.dptr(d_scale), mode, slen,
+                                      _lib.stream_ptr()),
+                "pt_dense_apply_eo",
+            )
+            return d_y
         _lib.check(
             lib.pt_dense_apply(_lib.dptr(self._packed_device()), n, n, _lib.dptr(d_u),
                                _lib.dptr(d_y), after, before, float(alpha), float(beta),
@@ -239,6 +281,15 @@ class _DiffMat(np.ndarray):
         """``alpha * D u + beta * c`` stored through the pencil-redistribution map ``smap``
         (``pt_dense_apply_scatter``: the epilogue writes into the peers' buffers)."""
         lib = _lib.load()
+        eo = self._eo_forms() if EVEN_ODD else None
+        if eo is not None:
+            _lib.check(
+                lib.pt_dense_apply_eo_scatter(_lib.dptr(eo[1]), _lib.dptr(eo[2]), n, eo[0], _lib.dptr(d_u),
+                                              _lib.dptr(c), after, before, float(alpha), float(beta),
+                                              ctypes.byref(smap), _lib.stream_ptr()),
+                "pt_dense_apply_eo_scatter",
+            )
+            return
         _lib.check(
             lib.pt_dense_apply_scatter(_lib.dptr(self._packed_device()), n, n, _lib.dptr(d_u), _lib.dptr(c),
                                        after, before, float(alpha), float(beta), ctypes.byref(smap),
@@ -342,6 +393,9 @@ class ChebMat(_DiffMat):
         if weights == "cgl":
             _lib.check(lib.pt_gen_chebmat(_lib.dptr(d_x), n, order, _lib.dptr(d_mat),
                                           _lib.stream_ptr()), "pt_gen_chebmat")
+            # flipping trick: exactly centro(anti)symmetric on the symmetric CGL set
+            _lib.check(lib.pt_flip_symmetrize(_lib.dptr(d_mat), n, 1 if order % 2 == 0 else -1,
+                                              _lib.stream_ptr()), "pt_flip_symmetrize")
         else:
             # nodes from a non-affine mapper: polynomial collocation with barycentric weights
             work = _lib.empty((2 * n,))

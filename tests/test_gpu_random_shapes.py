@@ -142,7 +142,7 @@ def test_scatter_maps_random_single_rank():
     rng = np.random.default_rng(31)
     for trial in range(16):
         nd = int(rng.integers(1, 4))                       # destinations
-        chunk = int(rng.integers(1, 9)) * (2 if trial % 2 == 0 else 1)
+        chunk = int(rng.integers(1, 9)) * (2 if trial % 2 == 0 else 1) * (3 if trial % 3 == 0 else 1)
         n = nd * chunk - int(rng.integers(0, min(chunk, 3)))   # last destination may be ragged
         before = int(rng.choice([1, 2, 3, 4, 6]))
         a_inner = int(rng.integers(1, 4))
@@ -167,6 +167,8 @@ def test_scatter_maps_random_single_rank():
         m.base = table.data_ptr()
 
         D = rng.standard_normal((n, n))
+        if trial % 3 == 0 and n >= 16:
+            D = oracle.flip_symmetrize(D, -1)               # goes through pt_dense_apply_eo_scatter
         U = rng.standard_normal(after * n * before)
         C = rng.standard_normal(after * n * before)
         op = _DiffMat._wrap(torch.from_numpy(D).cuda(), (before, n, after), 1, 1, None)

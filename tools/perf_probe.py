@@ -73,8 +73,37 @@ def fourier(npts, axis, batch, label, order=1):
                           "dense_equiv_tflops": round(2.0 * n * P * batch / ms * 1e-9, 1)}))
 
 
+def real_op(kind, n, order, npts, axis, batch, label):
+    """Real (centrosymmetric) operators: even-odd kernel vs the plain kernel."""
+    import pytristan_b200.operators as ops_mod
+    x = np.arange(n) * (2 * np.pi / n) if kind == "four" else pt.cheb(n, -1.0, 1.0)
+    op = pt.FourMat(x, order=order) if kind == "four" else pt.ChebMat(x, order=order)
+    op.npts, op.axis = tuple(npts), axis
+    P = int(np.prod(npts))
+    U = torch.randn(batch, P, dtype=torch.float64, device="cuda")
+    Y = torch.empty_like(U)
+    fl = 2.0 * n * P * batch
+    for eo in (True, False):
+        ops_mod.EVEN_ODD = eo
+        op.apply(U, out=Y)
+        ms = timeit(lambda: op.apply(U, out=Y))
+        print(json.dumps({"case": f"{label} [{'even-odd' if eo else 'plain'}]", "ms": round(ms, 4),
+                          "dense_form_tflops": round(fl / ms * 1e-9, 2), "executed_tflops": round(fl / ms * 1e-9 / (2 if eo else 1), 2),
+                          "executed_frac_peak": round(fl / ms * 1e-9 / (2 if eo else 1) / PEAK_TF, 3), "gpts_s": round(P * batch / ms * 1e-6, 2)}))
+    ops_mod.EVEN_ODD = True
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "eo":
+        real_op("four", 1024, 1, (1024, 257), 0, 64, "cfg2 d/dx FourMat K2 n=1024")
+        real_op("cheb", 257, 2, (1024, 257), 1, 64, "cfg2 d2/dy2 ChebMat K1 n=257")
+        real_op("cheb", 512, 2, (1024, 512), 1, 16, "cfg3 radial-like K1 n=512")
+        real_op("cheb", 2048, 1, (8192, 2048), 1, 1, "cfg5a-1/8 ChebMat K1 n=2048")
+        real_op("cheb", 512, 2, (512, 512, 512), 0, 1, "cfg5b x K2 n=512")
+        real_op("cheb", 512, 2, (512, 512, 512), 1, 1, "cfg5b y K1 n=512")
+        real_op("four", 1024, 2, (1024, 512), 0, 1, "cfg3 B=1 azimuthal K2 n=1024")
+        sys.exit(0)
     if what == "fftcfg":
         lib = _lib.load()
         for cfg in (0, 1):
