@@ -388,12 +388,20 @@ def run_gpu(args, spec):
 
         tf = ctypes.c_double(0.0)
         _lib.check(lib.pt_measure_dmma_peak(ctypes.byref(tf), 4000), "pt_measure_dmma_peak")
-        achieved = alg / (per_op_ms[dom] * 1e-3) * 1e-12
-        roof = {"bound": "tensor", "kernel": label, "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
+        dense_form = alg / (per_op_ms[dom] * 1e-3) * 1e-12
+        # a centrosymmetric operator runs as two half-size products (even-odd decomposition): the
+        # kernel EXECUTES half the flops of the dense form; the roofline fraction is on executed flops
+        eo = bool(getattr(ops[dom], "even_odd", False))
+        ratio = ops[dom].executed_flop_ratio() if hasattr(ops[dom], "executed_flop_ratio") else (0.5 if eo else 1.0)
+        eo = eo or ratio < 1.0
+        achieved = dense_form * ratio
+        roof = {"bound": "tensor", "kernel": label + (" [even-odd: two half-size DMMA products]" if eo else ""),
+                "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
                 "frac": achieved / tf.value, "traffic": traffic,
                 "peak_source": "FP64 DMMA m8n8k4 register-resident loop measured live on this GPU "
                                "(pt_measure_dmma_peak); MEASURED_PEAKS.json has no FP64 entry",
-                "alg_flops_per_launch": alg, "avg_launch_ms": per_op_ms[dom]}
+                "alg_flops_per_launch": alg, "executed_flops_per_launch": alg * ratio,
+                "dense_form_tflops": dense_form, "even_odd": eo, "avg_launch_ms": per_op_ms[dom]}
     else:
         hbm = peaks.get("hbm_gbs", 6650.0)
         achieved = alg / (per_op_ms[dom] * 1e-3) * 1e-9
@@ -567,9 +575,12 @@ def run_gpu_sharded(args, spec):
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                     "note": "per-GPU algorithmic bytes of the whole step (3 derivatives: 16 B/pt each, or 32 B/pt for the fused gradient) over the step time, halo traffic included"}
         else:
-            ach = local_alg / (ms * 1e-3) * 1e-12
+            dense_form = local_alg / (ms * 1e-3) * 1e-12
+            eo = all(bool(getattr(o, "even_odd", False)) for o in ops)
+            ach = dense_form * (0.5 if eo else 1.0)
             roof = {"bound": "tensor", "achieved": ach, "peak": 37.0, "unit": "TFLOP/s", "frac": ach / 37.0, "traffic": None,
-                    "note": "per-GPU algorithmic flops of the three applies over the whole step time (all-to-all rounds included); peak = measured FP64 DMMA 37.0 (profiles/r01_fp64_peak.json)"}
+                    "dense_form_tflops": dense_form, "even_odd": eo,
+                    "note": "per-GPU EXECUTED tensor flops of the three applies (half the dense form when the operators run the even-odd kernel) over the whole step time (redistribution included); peak = measured FP64 DMMA 37.0 (profiles/r01_fp64_peak.json)"}
         line = {"metric": "derivative grid-points/sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
@@ -596,12 +607,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="channel_1024x257_b64")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-even-odd", action="store_true",
+                    help="apply centrosymmetric operators with the plain full-size kernel (A/B against the default)")
     ap.add_argument("--fused-gradient", action="store_true",
                     help="slab workload: the three derivatives in one read of the field (pt_stencil_grad3_halo)")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="sharded workloads: peer-memory kernels (default) or the NCCL exchange/all_to_all path")
     args = ap.parse_args()
     spec = workload_spec(args.workload)
+    if args.no_even_odd and args.impl != "reference":
+        import pytristan_b200.operators as ops_mod
+
+        ops_mod.EVEN_ODD = False
     if args.impl == "reference":
         run_reference(args, spec)
     elif spec.get("kind") in ("slab", "pencil"):

@@ -399,6 +399,8 @@ def polar_laplacian(theta, r, U):
     h = (theta[-1] - theta[0]) / (nt - 1)
     D2t = four_mat(nt, nt * h, 2)
     Ar = cheb_mat(r, 2) + cheb_mat(r, 1) / r[:, None]
+    if np.max(np.abs(r + r[::-1])) <= 8.0 * np.finfo(np.float64).eps * np.max(np.abs(r)):
+        Ar = flip_symmetrize(Ar, 1)       # radial nodes symmetric about 0: same rule as PolarLaplacian
     U = np.asarray(U, dtype=np.float64)
     Y = apply_along_axis(Ar, U, (nt, nr), 1)
     T = apply_along_axis(D2t, U, (nt, nr), 0)

@@ -469,8 +469,11 @@ template <bool KCONTIG, bool VEC16, bool SCAT>
 int launch_eo_shape(EoParams& p, cudaStream_t stream) {
   // CTAs of the large tile; below one per SM the small tile fills the GPU better
   const int64_t ctas = ((p.H + 63) / 64) * ((p.NN + 63) / 64);
-  const int cfg = g_eo_config >= 0 ? g_eo_config : (ctas < pt::sm_count() ? 1 : 0);
+  // measured on B200 (tools/perf_probe.py eocfg): the 1 x 4 warp layout (half as many E/O adds per
+  // DMMA) is 1-6 % faster than 2 x 2
+  const int cfg = g_eo_config >= 0 ? g_eo_config : (ctas < pt::sm_count() ? 1 : 2);
   if (cfg == 1) return launch_eo<2, 2, 2, 2, 4, 3, KCONTIG, VEC16, 4, SCAT>(p, stream);   // 32 half-rows x 32 columns
+  if (cfg == 2) return launch_eo<1, 4, 8, 2, 4, 3, KCONTIG, VEC16, 2, SCAT>(p, stream);   // 64 x 64, warps side by side
   return launch_eo<2, 2, 4, 4, 4, 3, KCONTIG, VEC16, 2, SCAT>(p, stream);                 // 64 half-rows x 64 columns
 }
 

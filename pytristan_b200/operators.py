@@ -203,6 +203,11 @@ class _DiffMat(np.ndarray):
                         break
         return self._eo or None
 
+    @property
+    def even_odd(self):
+        """True when ``apply`` runs the even-odd kernel (centrosymmetric operator, EVEN_ODD on)."""
+        return bool(EVEN_ODD and self._band is None and self._eo_forms() is not None)
+
     # -- geometry -----------------------------------------------------------------------------------
     def _split(self, size, npts=None, axis=None):
         npts = self.npts if npts is None else tuple(npts)
@@ -609,6 +614,11 @@ class PolarLaplacian:
         _lib.require_cuda()
         d_r = _lib.to_device(r)
         radial_mat = d2.device() + d1.device() / d_r[:, None]
+        if radial == "cheb" and np.max(np.abs(r + r[::-1])) <= 8.0 * np.finfo(np.float64).eps * np.max(np.abs(r)):
+            # radial nodes symmetric about r = 0 (fornberg=True): D2 + D1/r is centrosymmetric; the
+            # flipping trick makes it exactly so (the 1/r rows differ by an ulp of r otherwise)
+            _lib.check(_lib.load().pt_flip_symmetrize(_lib.dptr(radial_mat), int(r.size), 1, _lib.stream_ptr()),
+                       "pt_flip_symmetrize")
         self.radial = _DiffMat._wrap(radial_mat, self.npts, 1, 2, grid.num)
         # azimuthal="fft": D2_theta through pt_fourier_apply (1/r^2 still fused in its epilogue)
         self.azimuthal = FourMat(grid, axis=0, order=2, method=azimuthal)
@@ -622,6 +632,22 @@ class PolarLaplacian:
         if kind == "numpy":
             return d_y.cpu().numpy().reshape(np.shape(u))
         return d_y.view(d_u.shape)
+
+    @property
+    def even_odd(self):
+        """True when every dense pass of the Laplacian runs the even-odd kernel."""
+        az = self.azimuthal
+        return bool(self.radial.even_odd and (getattr(az, "method", "dense") == "fft" or az.even_odd))
+
+    def executed_flop_ratio(self):
+        """Executed / dense-form tensor-core flops of one application (0.5 per pass that runs the
+        even-odd kernel; an FFT azimuthal pass counts on neither side)."""
+        nt, nr = int(self.npts[0]), int(self.npts[1])
+        dense = nr + (0 if getattr(self.azimuthal, "method", "dense") == "fft" else nt)
+        done = nr * (0.5 if self.radial.even_odd else 1.0)
+        if getattr(self.azimuthal, "method", "dense") != "fft":
+            done += nt * (0.5 if self.azimuthal.even_odd else 1.0)
+        return done / dense
 
     # the two methods the host pipeline (apply_host) and the benchmarks drive operators through
     def _split(self, size):
