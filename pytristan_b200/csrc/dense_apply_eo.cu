@@ -30,7 +30,8 @@ struct EoParams {
   ScatterDev sc;
   int n, H;                         // operator size, half size ceil(n/2)
   int MPH, KPH;                     // padded half rows, k-panels of the half problem
-  int rt_per_block, m_blocks;       // row-tiles (8 half-rows) per CTA
+  int rt_per_block, m_blocks;       // row-tiles (8 half-rows) per tile, tiles along the half-rows
+  int64_t total_tiles;              // m_blocks * column tiles
   int sign;                         // +1: J D J = D, -1: J D J = -D
   int64_t before, NN, slab;         // slab = n*before
   double alpha, beta;
@@ -135,18 +136,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wn = warp % WARPS_N, wm = warp / WARPS_N;
   const int g = lane >> 2, t = lane & 3;
-
-  const int m_block = blockIdx.x % p.m_blocks;
-  const int64_t n_block = blockIdx.x / p.m_blocks;
   const int rtiles_total = p.MPH >> 3;
-  const int rt0 = m_block * p.rt_per_block;
-  const int rt_count = min(p.rt_per_block, rtiles_total - rt0);
-  const int m0h = rt0 * 8;                      // first half-row of the CTA
-  const int rows_blk = rt_count * 8;
-  const int64_t n0 = n_block * C::BN;
-  const int q = (rt_count + WARPS_M - 1) / WARPS_M;
-  const int my_rt0 = wm * q;
-  const int my_rt = max(0, min(q, rt_count - my_rt0));
   const int nchunks = (p.KPH + BKP - 1) / BKP;
   const int n = p.n;
 
@@ -157,20 +147,63 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
   static_assert(!KCONTIG || (C::NT % CPR2 == 0 && C::BN % RPP2 == 0), "K2 loader shape");
   constexpr int APIECES = C::BMH * 2;                                // 16-byte pieces of one panel half
   constexpr int ASUB = (APIECES + C::NT - 1) / C::NT;
-
-  // ---- loader: per-thread constants -----------------------------------------------------------------
   const int b_cc = KCONTIG ? tid % CPR2 : tid % CPR1;
   const int b_r0 = KCONTIG ? tid / CPR2 : tid / CPR1;
+  const int64_t a_panel = int64_t(p.MPH) * 4;
+  const int fast_chunks = min(p.KPH / BKP, n / C::BK);   // all panels valid and all k + EPC <= n
+
+  // The CTA is persistent: it walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... and its loader
+  // runs STAGES-1 chunks ahead of the DMMAs ACROSS tile boundaries, so the pipeline is never refilled
+  // from empty and the epilogue of a tile overlaps the loads of the next one.
+  // ---- loader state (tile ld_tile, next chunk ld_chunk) ---------------------------------------------
+  int64_t ld_tile = blockIdx.x;
+  int ld_chunk = 0;
+  int ld_m0h = 0, ld_rows = 0;
+  int64_t ld_n0 = 0;
   const double* b_base = p.U;                   // K1: address of (a, k = 0, b) of this thread's column chunk
   bool b_col_ok = false;
-  if (!KCONTIG) {
-    const int64_t nn = n0 + int64_t(b_cc) * EPC;
-    b_col_ok = nn < p.NN;
-    if (b_col_ok) {
-      const int64_t a = nn / p.before;
-      b_base = p.U + a * p.slab + (nn - a * p.before);
+  const double *ae_ptr = p.Dpe, *ao_ptr = p.Dpo, *b1_ptr = p.U, *b2_ptr = p.U;
+  int64_t b_rstep = 0, b_cstep = 0;
+  unsigned a_ok = 0, a_in = 0, b_ok = 0;
+
+  auto setup_loader = [&](int64_t tile) {
+    const int m_block = int(tile % p.m_blocks);
+    const int64_t n_block = tile / p.m_blocks;
+    const int rt0 = m_block * p.rt_per_block;
+    ld_m0h = rt0 * 8;
+    ld_rows = min(p.rt_per_block, rtiles_total - rt0) * 8;
+    ld_n0 = n_block * C::BN;
+    ae_ptr = p.Dpe + size_t(ld_m0h) * 4 + tid * 2;
+    ao_ptr = p.Dpo + size_t(ld_m0h) * 4 + tid * 2;
+    a_ok = 0; a_in = 0; b_ok = 0;
+#pragma unroll
+    for (int sub = 0; sub < ASUB; ++sub) {
+      if (((tid + sub * C::NT) >> 1) < ld_rows) a_ok |= 1u << sub;
+      if (tid + sub * C::NT < APIECES) a_in |= 1u << sub;
     }
-  }
+    if (!KCONTIG) {
+      const int64_t nn = ld_n0 + int64_t(b_cc) * EPC;
+      b_col_ok = nn < p.NN;
+      b_base = p.U;
+      if (b_col_ok) {
+        const int64_t a = nn / p.before;
+        b_base = p.U + a * p.slab + (nn - a * p.before);
+      }
+      b1_ptr = b_base + int64_t(b_r0) * p.before;
+      b2_ptr = b_base + int64_t(n - 1 - b_r0) * p.before;
+      b_rstep = int64_t(RPP1) * p.before;            // tile 2 walks the rows downwards
+      b_cstep = int64_t(C::BK) * p.before;
+      b_ok = b_col_ok ? ~0u : 0u;
+    } else {
+      b1_ptr = p.U + (ld_n0 + b_r0) * n + b_cc * EPC;
+      b2_ptr = p.U + (ld_n0 + b_r0) * n + (n - EPC - b_cc * EPC);
+      b_rstep = int64_t(RPP2) * n;                   // next column: both tiles move the same way
+      b_cstep = C::BK;
+#pragma unroll
+      for (int r = 0; r < C::BN / RPP2; ++r)
+        if (ld_n0 + b_r0 + r * RPP2 < p.NN) b_ok |= 1u << r;
+    }
+  };
 
   // generic (bounds-checked) loader: the chunk that crosses the end of the k range, tiny operators
   auto load_stage_edge = [&](int stage, int chunk) {
@@ -185,8 +218,8 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
       for (int sub = 0; sub < ASUB; ++sub) {
         const int c = tid + sub * C::NT;
         if (APIECES % C::NT == 0 || c < APIECES) {
-          const bool ok = (kp0 + pp < p.KPH) && ((c >> 1) < rows_blk);
-          const size_t off = (size_t(kp0 + pp) * p.MPH + m0h) * 4 + c * 2;
+          const bool ok = (kp0 + pp < p.KPH) && ((c >> 1) < ld_rows);
+          const size_t off = (size_t(kp0 + pp) * p.MPH + ld_m0h) * 4 + c * 2;
           cp_async16(As + (pp * 2 * C::BMH) * 4 + c * 2, ok ? p.Dpe + off : p.Dpe, ok ? 16 : 0);
           cp_async16(As + (pp * 2 * C::BMH + C::BMH) * 4 + c * 2, ok ? p.Dpo + off : p.Dpo, ok ? 16 : 0);
         }
@@ -211,7 +244,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
 #pragma unroll
       for (int r = 0; r < C::BN / RPP2; ++r) {
         const int col = b_r0 + r * RPP2;
-        const int64_t nn = n0 + col;
+        const int64_t nn = ld_n0 + col;
         // the piece k .. k+EPC-1 and its mirror n-EPC-k .. n-1-k lie inside the row iff k+EPC <= n
         const bool ok = (nn < p.NN) && (k + EPC <= n);
         const double* row = p.U + nn * n;
@@ -229,37 +262,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
   };
 
   // fast loader for chunks whose panels are all valid: running pointers, no index arithmetic in
-  // the loop (chunks are loaded in increasing order) — the loader burst is what keeps a warp away
-  // from the tensor pipe
-  const int64_t a_panel = int64_t(p.MPH) * 4;
-  const double* ae_ptr = p.Dpe + size_t(m0h) * 4 + tid * 2;
-  const double* ao_ptr = p.Dpo + size_t(m0h) * 4 + tid * 2;
-  unsigned a_ok = 0, a_in = 0;
-#pragma unroll
-  for (int sub = 0; sub < ASUB; ++sub) {
-    if (((tid + sub * C::NT) >> 1) < rows_blk) a_ok |= 1u << sub;
-    if (tid + sub * C::NT < APIECES) a_in |= 1u << sub;
-  }
-  const double *b1_ptr, *b2_ptr;
-  int64_t b_rstep, b_cstep;
-  unsigned b_ok = 0;
-  if (!KCONTIG) {
-    b1_ptr = b_base + int64_t(b_r0) * p.before;
-    b2_ptr = b_base + int64_t(n - 1 - b_r0) * p.before;
-    b_rstep = int64_t(RPP1) * p.before;            // tile 2 walks the rows downwards
-    b_cstep = int64_t(C::BK) * p.before;
-    b_ok = b_col_ok ? ~0u : 0u;
-  } else {
-    b1_ptr = p.U + (n0 + b_r0) * n + b_cc * EPC;
-    b2_ptr = p.U + (n0 + b_r0) * n + (n - EPC - b_cc * EPC);
-    b_rstep = int64_t(RPP2) * n;                   // next column: both tiles move the same way
-    b_cstep = C::BK;
-#pragma unroll
-    for (int r = 0; r < C::BN / RPP2; ++r)
-      if (n0 + b_r0 + r * RPP2 < p.NN) b_ok |= 1u << r;
-  }
-  const int fast_chunks = min(p.KPH / BKP, n / C::BK);   // all panels valid and all k + EPC <= n
-
+  // the loop (the chunks of a tile are loaded in increasing order)
   auto load_stage = [&](int stage, int chunk) {
     if (chunk >= fast_chunks) { load_stage_edge(stage, chunk); return; }
     double* As = smem + size_t(stage) * C::STAGE;
@@ -293,112 +296,134 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
     b2_ptr -= b_cstep;
   };
 
-  double acce[WR][WN][2], acco[WR][WN][2];
-#pragma unroll
-  for (int i = 0; i < WR; ++i)
-#pragma unroll
-    for (int j = 0; j < WN; ++j) { acce[i][j][0] = acce[i][j][1] = 0.0; acco[i][j][0] = acco[i][j][1] = 0.0; }
-
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nchunks) load_stage(s, s);
+  // issue the next chunk of the flattened (tile, chunk) sequence into ring slot `slot`
+  auto issue_next = [&](int slot) {
+    if (ld_tile < p.total_tiles) {
+      load_stage(slot, ld_chunk);
+      if (++ld_chunk == nchunks) {
+        ld_chunk = 0;
+        ld_tile += gridDim.x;
+        if (ld_tile < p.total_tiles) setup_loader(ld_tile);
+      }
+    }
     cp_async_commit();
-  }
+  };
 
-  const int a_off = my_rt0 * 32 + lane;
+  if (ld_tile < p.total_tiles) setup_loader(ld_tile);
+  unsigned issued = 0, consumed = 0;            // ring positions
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) { issue_next(issued % STAGES); ++issued; }
+
   // B fragment: k = t, column = g.  In the mirrored tile of the contiguous-axis kernel a 16-byte
   // piece holds (u[n-2-k], u[n-1-k]): the slot of mirrored index k is k ^ 1.
   const int b1_off = KCONTIG ? ((wn * WN * 8 + g) * C::PB + t) : (t * C::PB + wn * WN * 8 + g);
   const int b2_off = KCONTIG ? ((wn * WN * 8 + g) * C::PB + (VEC16 ? (t ^ 1) : t)) : b1_off;
   const int nfull = p.KPH / BKP;
   const int tail = p.KPH - nfull * BKP;
-
-  for (int kc = 0; kc < nchunks; ++kc) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    {
-      const int nxt = kc + STAGES - 1;
-      if (nxt < nchunks) load_stage(nxt % STAGES, nxt);
-      cp_async_commit();
-    }
-    const double* As = smem + size_t(kc % STAGES) * C::STAGE;
-    const double* B1 = As + C::A_STAGE;
-    const double* B2 = B1 + C::B_TILE;
-    EoDispatch<C, WR, WR, WN, BKP, KCONTIG, VEC16>::run(my_rt, As + a_off, B1 + b1_off, B2 + b2_off,
-                                                        kc < nfull ? BKP : tail, acce, acco);
-  }
-  cp_async_wait<0>();
-
-  // ---- epilogue: rows i (ze + zo) and n-1-i (s*(ze - zo)) ----------------------------------------------
   const bool use_beta = (p.beta != 0.0);
   const double sgn = double(p.sign);
+
+  for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int m_block = int(tile % p.m_blocks);
+    const int64_t n_block = tile / p.m_blocks;
+    const int rt0 = m_block * p.rt_per_block;
+    const int rt_count = min(p.rt_per_block, rtiles_total - rt0);
+    const int m0h = rt0 * 8;                      // first half-row of the tile
+    const int64_t n0 = n_block * C::BN;
+    const int q = (rt_count + WARPS_M - 1) / WARPS_M;
+    const int my_rt0 = wm * q;
+    const int my_rt = max(0, min(q, rt_count - my_rt0));
+    const int a_off = my_rt0 * 32 + lane;
+
+    double acce[WR][WN][2], acco[WR][WN][2];
 #pragma unroll
-  for (int j = 0; j < WN; ++j) {
-    const int64_t nn = n0 + (wn * WN + j) * 8 + 2 * t;
-    if (nn >= p.NN) continue;
-    const bool two = (nn + 1 < p.NN);
-    int64_t a0, b0, a1, b1;
-    if (KCONTIG) {
-      a0 = nn; b0 = 0; a1 = nn + 1; b1 = 0;
-    } else {
-      a0 = nn / p.before; b0 = nn - a0 * p.before;
-      if (b0 + 1 < p.before) { a1 = a0; b1 = b0 + 1; } else { a1 = a0 + 1; b1 = 0; }
-    }
-    double s0 = p.alpha, s1 = p.alpha;
-    if (p.scale_mode == PT_SCALE_AFTER) {
-      s0 *= p.scale[a0 % p.scale_len];
-      if (two) s1 *= p.scale[a1 % p.scale_len];
-    } else if (p.scale_mode == PT_SCALE_BEFORE) {
-      s0 *= p.scale[b0];
-      if (two) s1 *= p.scale[b1];
-    }
-    const int64_t l0 = a0 * p.slab + b0, l1 = a1 * p.slab + b1;
-    int64_t d0 = 0, d1 = 0;
-    if (SCAT) {
-      const int64_t q0 = a0 / p.sc.a_inner, q1 = a1 / p.sc.a_inner;
-      d0 = p.sc.offset + q0 * p.sc.s_outer + (a0 - q0 * p.sc.a_inner) * p.sc.s_inner + b0;
-      d1 = p.sc.offset + q1 * p.sc.s_outer + (a1 - q1 * p.sc.a_inner) * p.sc.s_inner + b1;
-    }
+    for (int i = 0; i < WR; ++i)
 #pragma unroll
-    for (int i = 0; i < WR; ++i) {
-      if (i >= my_rt) continue;
-      const int hrow = m0h + (my_rt0 + i) * 8 + g;
-      if (hrow >= p.H) continue;
+      for (int j = 0; j < WN; ++j) { acce[i][j][0] = acce[i][j][1] = 0.0; acco[i][j][0] = acco[i][j][1] = 0.0; }
+
+    for (int kc = 0; kc < nchunks; ++kc) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      issue_next(issued % STAGES);
+      ++issued;
+      const double* As = smem + size_t(consumed % STAGES) * C::STAGE;
+      const double* B1 = As + C::A_STAGE;
+      const double* B2 = B1 + C::B_TILE;
+      ++consumed;
+      EoDispatch<C, WR, WR, WN, BKP, KCONTIG, VEC16>::run(my_rt, As + a_off, B1 + b1_off, B2 + b2_off,
+                                                          kc < nfull ? BKP : tail, acce, acco);
+    }
+
+    // ---- epilogue: rows i (ze + zo) and n-1-i (s*(ze - zo)) --------------------------------------------
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int row = half == 0 ? hrow : n - 1 - hrow;
-        if (half == 1 && row == hrow) continue;          // middle row of an odd n: written once
-        double w0, w1;
-        if (half == 0) { w0 = __dadd_rn(acce[i][j][0], acco[i][j][0]); w1 = __dadd_rn(acce[i][j][1], acco[i][j][1]); }
-        else { w0 = __dmul_rn(sgn, __dsub_rn(acce[i][j][0], acco[i][j][0])); w1 = __dmul_rn(sgn, __dsub_rn(acce[i][j][1], acco[i][j][1])); }
-        double r0 = s0, r1 = s1;
-        if (p.scale_mode == PT_SCALE_ROW) { const double sr = p.scale[row]; r0 *= sr; r1 *= sr; }
-        double v0 = __dmul_rn(r0, w0), v1 = __dmul_rn(r1, w1);
-        const int64_t off = int64_t(row) * p.before;
-        const double* c0 = (SCAT ? p.C : p.Y) + l0 + off;
-        const double* c1 = (SCAT ? p.C : p.Y) + l1 + off;
-        double *y0, *y1;
-        if (SCAT) {
-          const int dq = row / p.sc.chunk;
-          double* db = p.sc.base[dq] + int64_t(row - dq * p.sc.chunk) * p.sc.s_i;
-          y0 = db + d0; y1 = db + d1;
-        } else {
-          y0 = p.Y + l0 + off; y1 = p.Y + l1 + off;
-        }
-        if (!KCONTIG && VEC16) {
-          if (use_beta) { const double2 o = *reinterpret_cast<const double2*>(c0); v0 = __fma_rn(p.beta, o.x, v0); v1 = __fma_rn(p.beta, o.y, v1); }
-          *reinterpret_cast<double2*>(y0) = make_double2(v0, v1);
-        } else {
-          if (use_beta) v0 = __fma_rn(p.beta, *c0, v0);
-          *y0 = v0;
-          if (two) {
-            if (use_beta) v1 = __fma_rn(p.beta, *c1, v1);
-            *y1 = v1;
+    for (int j = 0; j < WN; ++j) {
+      const int64_t nn = n0 + (wn * WN + j) * 8 + 2 * t;
+      if (nn >= p.NN) continue;
+      const bool two = (nn + 1 < p.NN);
+      int64_t a0, b0, a1, b1;
+      if (KCONTIG) {
+        a0 = nn; b0 = 0; a1 = nn + 1; b1 = 0;
+      } else {
+        a0 = nn / p.before; b0 = nn - a0 * p.before;
+        if (b0 + 1 < p.before) { a1 = a0; b1 = b0 + 1; } else { a1 = a0 + 1; b1 = 0; }
+      }
+      double s0 = p.alpha, s1 = p.alpha;
+      if (p.scale_mode == PT_SCALE_AFTER) {
+        s0 *= p.scale[a0 % p.scale_len];
+        if (two) s1 *= p.scale[a1 % p.scale_len];
+      } else if (p.scale_mode == PT_SCALE_BEFORE) {
+        s0 *= p.scale[b0];
+        if (two) s1 *= p.scale[b1];
+      }
+      const int64_t l0 = a0 * p.slab + b0, l1 = a1 * p.slab + b1;
+      int64_t d0 = 0, d1 = 0;
+      if (SCAT) {
+        const int64_t q0 = a0 / p.sc.a_inner, q1 = a1 / p.sc.a_inner;
+        d0 = p.sc.offset + q0 * p.sc.s_outer + (a0 - q0 * p.sc.a_inner) * p.sc.s_inner + b0;
+        d1 = p.sc.offset + q1 * p.sc.s_outer + (a1 - q1 * p.sc.a_inner) * p.sc.s_inner + b1;
+      }
+#pragma unroll
+      for (int i = 0; i < WR; ++i) {
+        if (i >= my_rt) continue;
+        const int hrow = m0h + (my_rt0 + i) * 8 + g;
+        if (hrow >= p.H) continue;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int row = half == 0 ? hrow : n - 1 - hrow;
+          if (half == 1 && row == hrow) continue;          // middle row of an odd n: written once
+          double w0, w1;
+          if (half == 0) { w0 = __dadd_rn(acce[i][j][0], acco[i][j][0]); w1 = __dadd_rn(acce[i][j][1], acco[i][j][1]); }
+          else { w0 = __dmul_rn(sgn, __dsub_rn(acce[i][j][0], acco[i][j][0])); w1 = __dmul_rn(sgn, __dsub_rn(acce[i][j][1], acco[i][j][1])); }
+          double r0 = s0, r1 = s1;
+          if (p.scale_mode == PT_SCALE_ROW) { const double sr = p.scale[row]; r0 *= sr; r1 *= sr; }
+          double v0 = __dmul_rn(r0, w0), v1 = __dmul_rn(r1, w1);
+          const int64_t off = int64_t(row) * p.before;
+          const double* c0 = (SCAT ? p.C : p.Y) + l0 + off;
+          const double* c1 = (SCAT ? p.C : p.Y) + l1 + off;
+          double *y0, *y1;
+          if (SCAT) {
+            const int dq = row / p.sc.chunk;
+            double* db = p.sc.base[dq] + int64_t(row - dq * p.sc.chunk) * p.sc.s_i;
+            y0 = db + d0; y1 = db + d1;
+          } else {
+            y0 = p.Y + l0 + off; y1 = p.Y + l1 + off;
+          }
+          if (!KCONTIG && VEC16) {
+            if (use_beta) { const double2 o = *reinterpret_cast<const double2*>(c0); v0 = __fma_rn(p.beta, o.x, v0); v1 = __fma_rn(p.beta, o.y, v1); }
+            *reinterpret_cast<double2*>(y0) = make_double2(v0, v1);
+          } else {
+            if (use_beta) v0 = __fma_rn(p.beta, *c0, v0);
+            *y0 = v0;
+            if (two) {
+              if (use_beta) v1 = __fma_rn(p.beta, *c1, v1);
+              *y1 = v1;
+            }
           }
         }
       }
     }
   }
+  cp_async_wait<0>();
 }
 
 // Ae / Ao of a centrosymmetric operator in the fragment-major layout of the apply kernel
@@ -439,6 +464,8 @@ __global__ void symmetry_kernel(const double* __restrict__ D, int n, int sign, u
 
 inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
 
+int g_eo_persist = 1;   // tuning hook: pt_debug_set_eo_config(50 / 51) = one CTA per tile / persistent
+
 template <int WARPS_M, int WARPS_N, int WR, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB, bool SCAT>
 int launch_eo(EoParams& p, cudaStream_t stream) {
   using C = EoCfg<WARPS_M, WARPS_N, WR, WN, BKP, STAGES, KCONTIG>;
@@ -456,8 +483,11 @@ int launch_eo(EoParams& p, cudaStream_t stream) {
   p.rt_per_block = (rtiles + p.m_blocks - 1) / p.m_blocks;
   p.m_blocks = (rtiles + p.rt_per_block - 1) / p.rt_per_block;
   const int64_t n_blocks = (p.NN + C::BN - 1) / C::BN;
-  const int64_t grid = n_blocks * p.m_blocks;
-  if (grid <= 0) return PT_OK;
+  p.total_tiles = n_blocks * p.m_blocks;
+  if (p.total_tiles <= 0) return PT_OK;
+  // persistent CTAs: one per resident slot (g_eo_persist = 0: one CTA per tile, for A/B timing)
+  int64_t grid = int64_t(pt::sm_count()) * MINB;
+  if (!g_eo_persist || grid > p.total_tiles) grid = p.total_tiles;
   if (grid > 2147483647LL) return pt::fail(PT_ERR_UNSUPPORTED, "pt_dense_apply_eo: grid too large");
   kern<<<unsigned(grid), C::NT, C::SMEM, stream>>>(p);
   return pt::check_launch("pt_dense_apply_eo");
@@ -498,7 +528,7 @@ int apply_eo_impl(const double* pe, const double* po, int n, int sign, const dou
   p.sign = sign;
   p.before = before; p.NN = after * before; p.slab = int64_t(n) * before;
   p.alpha = alpha; p.beta = beta; p.scale_mode = scale_mode; p.scale_len = scale_len > 0 ? scale_len : 1;
-  p.m_blocks = 1; p.rt_per_block = 1;
+  p.m_blocks = 1; p.rt_per_block = 1; p.total_tiles = 0;
   cudaStream_t st = pt::as_stream(stream);
   if (before == 1) {
     const bool vec = (n % 2 == 0) && aligned16(U);
@@ -517,7 +547,8 @@ int apply_eo_impl(const double* pe, const double* po, int n, int sign, const dou
 }  // namespace
 
 extern "C" int pt_debug_set_eo_config(int id) {
-  g_eo_config = id;
+  if (id == 50 || id == 51) g_eo_persist = id - 50;
+  else g_eo_config = id;
   return PT_OK;
 }
 

@@ -95,6 +95,17 @@ def real_op(kind, n, order, npts, axis, batch, label):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "eopersist":
+        lib = _lib.load()
+        for mode in (50, 51):
+            lib.pt_debug_set_eo_config(mode)
+            print("== eo persistent", mode - 50)
+            real_op("four", 1024, 1, (1024, 257), 0, 64, "cfg2 d/dx FourMat K2 n=1024")
+            real_op("cheb", 257, 2, (1024, 257), 1, 64, "cfg2 d2/dy2 ChebMat K1 n=257")
+            real_op("cheb", 2048, 1, (8192, 2048), 1, 1, "cfg5a-1/8 ChebMat K1 n=2048")
+            real_op("cheb", 512, 2, (512, 512, 512), 1, 1, "cfg5b y K1 n=512")
+        lib.pt_debug_set_eo_config(51)
+        sys.exit(0)
     if what == "eocfg":
         lib = _lib.load()
         for cfg in (0, 2):
