@@ -95,6 +95,17 @@ def real_op(kind, n, order, npts, axis, batch, label):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "eosmall":
+        lib = _lib.load()
+        for cfg in (1, 2, 0):
+            lib.pt_debug_set_eo_config(cfg)
+            print("== eo config", cfg)
+            real_op("cheb", 512, 2, (1024, 512), 1, 1, "cfg3 B=1 radial K1 n=512")
+            real_op("four", 1024, 2, (1024, 512), 0, 1, "cfg3 B=1 azimuthal K2 n=1024")
+            real_op("cheb", 257, 2, (1024, 257), 1, 1, "cfg2 B=1 K1 n=257")
+            real_op("four", 1024, 1, (1024, 257), 0, 4, "cfg2 4 fields K2 n=1024 (e2e chunk)")
+        lib.pt_debug_set_eo_config(-1)
+        sys.exit(0)
     if what == "eopersist":
         lib = _lib.load()
         for mode in (50, 51):
