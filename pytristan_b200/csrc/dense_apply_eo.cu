@@ -21,7 +21,7 @@ using namespace ptdense;
 namespace {
 
 struct EoParams {
-  const double* __restrict__ Dpe;   // packed Ae: [KPH][MPH][4]
+  const double* __restrict__ Dpe;   // packed Ae: [KPH/2][MPH][8] (k-panel PAIRS, 8 consecutive k per row)
   const double* __restrict__ Dpo;   // packed Ao
   const double* __restrict__ U;
   double* __restrict__ Y;
@@ -29,7 +29,7 @@ struct EoParams {
   const double* __restrict__ scale;
   ScatterDev sc;
   int n, H;                         // operator size, half size ceil(n/2)
-  int MPH, KPH;                     // padded half rows, k-panels of the half problem
+  int MPH, KPH;                     // padded half rows, k-panels of the half problem (KPH is even)
   int rt_per_block, m_blocks;       // row-tiles (8 half-rows) per tile, tiles along the half-rows
   int64_t total_tiles;              // m_blocks * column tiles
   int sign;                         // +1: J D J = D, -1: J D J = -D
@@ -47,68 +47,81 @@ struct EoCfg {
   static constexpr int BMH = WARPS_M * WR * 8;                      // half-rows per CTA
   static constexpr int BN = WARPS_N * WN * 8;
   static constexpr int BK = BKP * 4;
-  static constexpr int A_STAGE = BKP * 2 * BMH * 4;                 // per panel: [even rows][odd rows] x 4
+  static constexpr int A_STAGE = BKP * 2 * BMH * 4;                 // per panel PAIR: [even rows][odd rows] x 8
   static constexpr int PB = KCONTIG ? (BK + 4) : (BN + 4);
   static constexpr int B_TILE = KCONTIG ? BN * PB : BK * PB;
   static constexpr int STAGE = A_STAGE + 2 * B_TILE;                // field tile + mirrored field tile
   static constexpr size_t SMEM = size_t(STAGES) * STAGE * sizeof(double);
 };
 
+// Fragments of one k-panel PAIR (8 consecutive k).  The operator is packed with the 8 k of a pair
+// contiguous per row, so ONE 16-byte load gives a lane its A elements of both panels of the pair:
+// the first panel takes k = 8P + 2t, the second k = 8P + 2t + 1 (any split of the 8 k into two
+// groups of 4 is a valid pair of DMMA k-panels); the field fragments follow the same assignment.
 template <class C, int RT, int WR, int WN, bool KCONTIG, bool VEC16>
-__device__ __forceinline__ void eo_frags(const double* As, const double* B1, const double* B2, int pp,
-                                         double (&ae)[WR], double (&ao)[WR], double (&be)[WN], double (&bo)[WN]) {
+__device__ __forceinline__ void eo_frags(const double* As, const double* B1, const double* B2, int pr,
+                                         double2 (&ae)[WR], double2 (&ao)[WR], double2 (&be)[WN], double2 (&bo)[WN]) {
 #pragma unroll
   for (int i = 0; i < RT; ++i) {
-    ae[i] = As[(pp * 2 * C::BMH + i * 8) * 4];
-    ao[i] = As[(pp * 2 * C::BMH + C::BMH + i * 8) * 4];
+    ae[i] = *reinterpret_cast<const double2*>(As + (pr * 2 * C::BMH + i * 8) * 8);
+    ao[i] = *reinterpret_cast<const double2*>(As + (pr * 2 * C::BMH + C::BMH + i * 8) * 8);
   }
-  // mirrored tile: 16-byte copies keep the memory order inside a pair, i.e. the pair is swapped
-  // with respect to the mirrored k index
 #pragma unroll
   for (int j = 0; j < WN; ++j) {
-    double f1, f2;
+    double f1a, f1b, f2a, f2b;     // a: k = 8P + 2t, b: k = 8P + 2t + 1 (B1/B2 already hold the lane's 2t offset)
     if (KCONTIG) {
-      f1 = B1[j * 8 * C::PB + pp * 4];
-      f2 = B2[j * 8 * C::PB + pp * 4];      // B2 already points at the (possibly pair-swapped) k slot
+      const double2 v1 = *reinterpret_cast<const double2*>(B1 + j * 8 * C::PB + pr * 8);
+      const double2 v2 = *reinterpret_cast<const double2*>(B2 + j * 8 * C::PB + pr * 8);
+      f1a = v1.x; f1b = v1.y;
+      // mirrored tile: 16-byte copies keep the memory order inside a pair, i.e. the pair is swapped
+      if (VEC16) { f2a = v2.y; f2b = v2.x; } else { f2a = v2.x; f2b = v2.y; }
     } else {
-      f1 = B1[pp * 4 * C::PB + j * 8];
-      f2 = B2[pp * 4 * C::PB + j * 8];
+      f1a = B1[pr * 8 * C::PB + j * 8]; f1b = B1[(pr * 8 + 1) * C::PB + j * 8];
+      f2a = B2[pr * 8 * C::PB + j * 8]; f2b = B2[(pr * 8 + 1) * C::PB + j * 8];
     }
-    be[j] = __dadd_rn(f1, f2);
-    bo[j] = __dsub_rn(f1, f2);
+    be[j] = make_double2(__dadd_rn(f1a, f2a), __dadd_rn(f1b, f2b));
+    bo[j] = make_double2(__dsub_rn(f1a, f2a), __dsub_rn(f1b, f2b));
   }
 }
 
 template <class C, int RT, int WR, int WN, int BKP, bool KCONTIG, bool VEC16>
-__device__ __forceinline__ void eo_compute(const double* As, const double* B1, const double* B2, int npanels,
+__device__ __forceinline__ void eo_compute(const double* As, const double* B1, const double* B2, int npairs,
                                            double (&acce)[WR][WN][2], double (&acco)[WR][WN][2]) {
-  if (npanels == BKP) {
-    double ae[2][WR], ao[2][WR], be[2][WN], bo[2][WN];
-    eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, 0, ae[0], ao[0], be[0], bo[0]);
+  static_assert(BKP % 2 == 0, "k-panels are processed in pairs");
+  if (npairs == BKP / 2) {
 #pragma unroll
-    for (int pp = 0; pp < BKP; ++pp) {
-      if (pp + 1 < BKP)
-        eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pp + 1, ae[(pp + 1) & 1], ao[(pp + 1) & 1],
-                                                 be[(pp + 1) & 1], bo[(pp + 1) & 1]);
+    for (int pr = 0; pr < BKP / 2; ++pr) {
+      double2 ae[WR], ao[WR], be[WN], bo[WN];
+      eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pr, ae, ao, be, bo);
+      // consecutive DMMAs share their A operand (operand reuse), as in the plain kernel
 #pragma unroll
-      for (int i = 0; i < RT; ++i)
+      for (int i = 0; i < RT; ++i) {
 #pragma unroll
-        for (int j = 0; j < WN; ++j) {
-          dmma(acce[i][j][0], acce[i][j][1], ae[pp & 1][i], be[pp & 1][j]);
-          dmma(acco[i][j][0], acco[i][j][1], ao[pp & 1][i], bo[pp & 1][j]);
-        }
+        for (int j = 0; j < WN; ++j) dmma(acce[i][j][0], acce[i][j][1], ae[i].x, be[j].x);
+#pragma unroll
+        for (int j = 0; j < WN; ++j) dmma(acco[i][j][0], acco[i][j][1], ao[i].x, bo[j].x);
+      }
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+#pragma unroll
+        for (int j = 0; j < WN; ++j) dmma(acce[i][j][0], acce[i][j][1], ae[i].y, be[j].y);
+#pragma unroll
+        for (int j = 0; j < WN; ++j) dmma(acco[i][j][0], acco[i][j][1], ao[i].y, bo[j].y);
+      }
     }
   } else {
 #pragma unroll 1
-    for (int pp = 0; pp < npanels; ++pp) {
-      double ae[WR], ao[WR], be[WN], bo[WN];
-      eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pp, ae, ao, be, bo);
+    for (int pr = 0; pr < npairs; ++pr) {
+      double2 ae[WR], ao[WR], be[WN], bo[WN];
+      eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pr, ae, ao, be, bo);
 #pragma unroll
       for (int i = 0; i < RT; ++i)
 #pragma unroll
         for (int j = 0; j < WN; ++j) {
-          dmma(acce[i][j][0], acce[i][j][1], ae[i], be[j]);
-          dmma(acco[i][j][0], acco[i][j][1], ao[i], bo[j]);
+          dmma(acce[i][j][0], acce[i][j][1], ae[i].x, be[j].x);
+          dmma(acco[i][j][0], acco[i][j][1], ao[i].x, bo[j].x);
+          dmma(acce[i][j][0], acce[i][j][1], ae[i].y, be[j].y);
+          dmma(acco[i][j][0], acco[i][j][1], ao[i].y, bo[j].y);
         }
     }
   }
@@ -118,9 +131,9 @@ __device__ __forceinline__ void eo_compute(const double* As, const double* B1, c
 template <class C, int RT, int WR, int WN, int BKP, bool KCONTIG, bool VEC16>
 struct EoDispatch {
   static __device__ __forceinline__ void run(int my_rt, const double* As, const double* B1, const double* B2,
-                                             int npanels, double (&acce)[WR][WN][2], double (&acco)[WR][WN][2]) {
-    if (my_rt == RT) eo_compute<C, RT, WR, WN, BKP, KCONTIG, VEC16>(As, B1, B2, npanels, acce, acco);
-    else EoDispatch<C, RT - 1, WR, WN, BKP, KCONTIG, VEC16>::run(my_rt, As, B1, B2, npanels, acce, acco);
+                                             int npairs, double (&acce)[WR][WN][2], double (&acco)[WR][WN][2]) {
+    if (my_rt == RT) eo_compute<C, RT, WR, WN, BKP, KCONTIG, VEC16>(As, B1, B2, npairs, acce, acco);
+    else EoDispatch<C, RT - 1, WR, WN, BKP, KCONTIG, VEC16>::run(my_rt, As, B1, B2, npairs, acce, acco);
   }
 };
 template <class C, int WR, int WN, int BKP, bool KCONTIG, bool VEC16>
@@ -145,11 +158,11 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
   constexpr int CPR2 = C::BK / EPC, RPP2 = C::NT / CPR2;            // K2: chunks per column, columns per pass
   static_assert(KCONTIG || (C::NT % CPR1 == 0 && C::BK % RPP1 == 0), "K1 loader shape");
   static_assert(!KCONTIG || (C::NT % CPR2 == 0 && C::BN % RPP2 == 0), "K2 loader shape");
-  constexpr int APIECES = C::BMH * 2;                                // 16-byte pieces of one panel half
+  constexpr int APIECES = C::BMH * 4;                                // 16-byte pieces of one panel-PAIR half (8 doubles per row)
   constexpr int ASUB = (APIECES + C::NT - 1) / C::NT;
   const int b_cc = KCONTIG ? tid % CPR2 : tid % CPR1;
   const int b_r0 = KCONTIG ? tid / CPR2 : tid / CPR1;
-  const int64_t a_panel = int64_t(p.MPH) * 4;
+  const int64_t a_panel = int64_t(p.MPH) * 8;             // one panel pair of the packed operator
   const int fast_chunks = min(p.KPH / BKP, n / C::BK);   // all panels valid and all k + EPC <= n
 
   // The CTA is persistent: it walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... and its loader
@@ -173,12 +186,12 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
     ld_m0h = rt0 * 8;
     ld_rows = min(p.rt_per_block, rtiles_total - rt0) * 8;
     ld_n0 = n_block * C::BN;
-    ae_ptr = p.Dpe + size_t(ld_m0h) * 4 + tid * 2;
-    ao_ptr = p.Dpo + size_t(ld_m0h) * 4 + tid * 2;
+    ae_ptr = p.Dpe + size_t(ld_m0h) * 8 + tid * 2;
+    ao_ptr = p.Dpo + size_t(ld_m0h) * 8 + tid * 2;
     a_ok = 0; a_in = 0; b_ok = 0;
 #pragma unroll
     for (int sub = 0; sub < ASUB; ++sub) {
-      if (((tid + sub * C::NT) >> 1) < ld_rows) a_ok |= 1u << sub;
+      if (((tid + sub * C::NT) >> 2) < ld_rows) a_ok |= 1u << sub;
       if (tid + sub * C::NT < APIECES) a_in |= 1u << sub;
     }
     if (!KCONTIG) {
@@ -211,17 +224,17 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
     double* B1 = As + C::A_STAGE;
     double* B2 = B1 + C::B_TILE;
     const int kp0 = chunk * BKP;
-    // operator panels: [pp][even rows | odd rows]
+    // operator panel pairs: [pr][even rows | odd rows] x 8
 #pragma unroll
-    for (int pp = 0; pp < BKP; ++pp)
+    for (int pr = 0; pr < BKP / 2; ++pr)
 #pragma unroll
       for (int sub = 0; sub < ASUB; ++sub) {
         const int c = tid + sub * C::NT;
         if (APIECES % C::NT == 0 || c < APIECES) {
-          const bool ok = (kp0 + pp < p.KPH) && ((c >> 1) < ld_rows);
-          const size_t off = (size_t(kp0 + pp) * p.MPH + ld_m0h) * 4 + c * 2;
-          cp_async16(As + (pp * 2 * C::BMH) * 4 + c * 2, ok ? p.Dpe + off : p.Dpe, ok ? 16 : 0);
-          cp_async16(As + (pp * 2 * C::BMH + C::BMH) * 4 + c * 2, ok ? p.Dpo + off : p.Dpo, ok ? 16 : 0);
+          const bool ok = (kp0 + 2 * pr < p.KPH) && ((c >> 2) < ld_rows);
+          const size_t off = (size_t(kp0 / 2 + pr) * p.MPH + ld_m0h) * 8 + c * 2;
+          cp_async16(As + (pr * 2 * C::BMH) * 8 + c * 2, ok ? p.Dpe + off : p.Dpe, ok ? 16 : 0);
+          cp_async16(As + (pr * 2 * C::BMH + C::BMH) * 8 + c * 2, ok ? p.Dpo + off : p.Dpo, ok ? 16 : 0);
         }
       }
     // field tiles: rows k (tile 1) and n-1-k (tile 2) for the 16 values of k of this chunk
@@ -269,18 +282,18 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
     double* B1 = As + C::A_STAGE;
     double* B2 = B1 + C::B_TILE;
 #pragma unroll
-    for (int pp = 0; pp < BKP; ++pp)
+    for (int pr = 0; pr < BKP / 2; ++pr)
 #pragma unroll
       for (int sub = 0; sub < ASUB; ++sub) {
         const bool ok = (a_ok >> sub) & 1u;
         if (APIECES % C::NT == 0 || ((a_in >> sub) & 1u)) {
           const int c2 = (tid + sub * C::NT) * 2;
-          cp_async16(As + (pp * 2 * C::BMH) * 4 + c2, ok ? ae_ptr + pp * a_panel + sub * C::NT * 2 : p.Dpe, ok ? 16 : 0);
-          cp_async16(As + (pp * 2 * C::BMH + C::BMH) * 4 + c2, ok ? ao_ptr + pp * a_panel + sub * C::NT * 2 : p.Dpo, ok ? 16 : 0);
+          cp_async16(As + (pr * 2 * C::BMH) * 8 + c2, ok ? ae_ptr + pr * a_panel + sub * C::NT * 2 : p.Dpe, ok ? 16 : 0);
+          cp_async16(As + (pr * 2 * C::BMH + C::BMH) * 8 + c2, ok ? ao_ptr + pr * a_panel + sub * C::NT * 2 : p.Dpo, ok ? 16 : 0);
         }
       }
-    ae_ptr += BKP * a_panel;
-    ao_ptr += BKP * a_panel;
+    ae_ptr += (BKP / 2) * a_panel;
+    ao_ptr += (BKP / 2) * a_panel;
     constexpr int BR = KCONTIG ? C::BN / RPP2 : C::BK / RPP1;
     constexpr int RPP = KCONTIG ? RPP2 : RPP1;
 #pragma unroll
@@ -316,10 +329,11 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
 
   // B fragment: k = t, column = g.  In the mirrored tile of the contiguous-axis kernel a 16-byte
   // piece holds (u[n-2-k], u[n-1-k]): the slot of mirrored index k is k ^ 1.
-  const int b1_off = KCONTIG ? ((wn * WN * 8 + g) * C::PB + t) : (t * C::PB + wn * WN * 8 + g);
-  const int b2_off = KCONTIG ? ((wn * WN * 8 + g) * C::PB + (VEC16 ? (t ^ 1) : t)) : b1_off;
+  // (the pair swap of the mirrored tile is undone when the fragments are read, eo_frags)
+  const int b1_off = KCONTIG ? ((wn * WN * 8 + g) * C::PB + 2 * t) : (2 * t * C::PB + wn * WN * 8 + g);
+  const int b2_off = b1_off;
   const int nfull = p.KPH / BKP;
-  const int tail = p.KPH - nfull * BKP;
+  const int tail = (p.KPH - nfull * BKP) / 2;        // panel pairs of the last, partial chunk
   const bool use_beta = (p.beta != 0.0);
   const double sgn = double(p.sign);
 
@@ -333,7 +347,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
     const int q = (rt_count + WARPS_M - 1) / WARPS_M;
     const int my_rt0 = wm * q;
     const int my_rt = max(0, min(q, rt_count - my_rt0));
-    const int a_off = my_rt0 * 32 + lane;
+    const int a_off = my_rt0 * 64 + 2 * lane;        // 8 rows x 8 k per row-tile and panel pair; lane (g, t) -> row g, k 2t
 
     double acce[WR][WN][2], acco[WR][WN][2];
 #pragma unroll
@@ -351,7 +365,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
       const double* B2 = B1 + C::B_TILE;
       ++consumed;
       EoDispatch<C, WR, WR, WN, BKP, KCONTIG, VEC16>::run(my_rt, As + a_off, B1 + b1_off, B2 + b2_off,
-                                                          kc < nfull ? BKP : tail, acce, acco);
+                                                          kc < nfull ? BKP / 2 : tail, acce, acco);
     }
 
     // ---- epilogue: rows i (ze + zo) and n-1-i (s*(ze - zo)) --------------------------------------------
@@ -429,13 +443,14 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
 // Ae / Ao of a centrosymmetric operator in the fragment-major layout of the apply kernel
 __global__ void pack_eo_kernel(const double* __restrict__ D, int n, int H, int MPH, int KPH,
                                double* __restrict__ pe, double* __restrict__ po) {
-  const int64_t total = int64_t(KPH) * MPH * 4;
+  // [KPH/2 panel pairs][MPH rows][8 consecutive k]
+  const int64_t total = int64_t(KPH / 2) * MPH * 8;
   const int mid = (n & 1) ? (n - 1) / 2 : -1;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
-    const int kk = int(idx & 3);
-    const int64_t r = idx >> 2;
-    const int i = int(r % MPH), k = int(r / MPH) * 4 + kk;
+    const int kk = int(idx & 7);
+    const int64_t r = idx >> 3;
+    const int i = int(r % MPH), k = int(r / MPH) * 8 + kk;
     double ve = 0.0, vo = 0.0;
     if (i < H && k < H) {
       const double a = D[int64_t(i) * n + k], b = D[int64_t(i) * n + (n - 1 - k)];
@@ -524,7 +539,7 @@ int apply_eo_impl(const double* pe, const double* po, int n, int sign, const dou
              : ScatterDev{nullptr, 1, 1, 0, 0, 0, 0};
   p.n = n; p.H = (n + 1) / 2;
   p.MPH = 8 * ((p.H + 7) / 8);
-  p.KPH = (p.H + 3) / 4;
+  p.KPH = 2 * ((p.H + 7) / 8);           // k-panels, padded to whole pairs
   p.sign = sign;
   p.before = before; p.NN = after * before; p.slab = int64_t(n) * before;
   p.alpha = alpha; p.beta = beta; p.scale_mode = scale_mode; p.scale_len = scale_len > 0 ? scale_len : 1;
@@ -555,7 +570,7 @@ extern "C" int pt_debug_set_eo_config(int id) {
 extern "C" int64_t pt_packed_eo_size(int n) {
   if (n <= 0) return 0;
   const int64_t H = (int64_t(n) + 1) / 2;
-  return ((H + 3) / 4) * (8 * ((H + 7) / 8)) * 4;
+  return ((H + 7) / 8) * (8 * ((H + 7) / 8)) * 8;
 }
 
 extern "C" int pt_operator_symmetry(const double* D, int n, int sign, double* worst_host, pt_stream_t stream) {
@@ -583,8 +598,8 @@ extern "C" int pt_operator_pack_eo(const double* D, int n, double* packed_even, 
                                    pt_stream_t stream) {
   PT_REQUIRE(D && packed_even && packed_odd, "pt_operator_pack_eo: null pointer");
   PT_REQUIRE(n >= 2, "pt_operator_pack_eo: n=%d", n);
-  const int H = (n + 1) / 2, MPH = 8 * ((H + 7) / 8), KPH = (H + 3) / 4;
-  const int64_t total = int64_t(KPH) * MPH * 4;
+  const int H = (n + 1) / 2, MPH = 8 * ((H + 7) / 8), KPH = 2 * ((H + 7) / 8);
+  const int64_t total = int64_t(KPH / 2) * MPH * 8;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_eo_kernel<<<unsigned(blocks), 256, 0, pt::as_stream(stream)>>>(D, n, H, MPH, KPH, packed_even, packed_odd);
