@@ -516,9 +516,13 @@ int launch_eo_shape(EoParams& p, cudaStream_t stream) {
   const int64_t ctas = ((p.H + 63) / 64) * ((p.NN + 63) / 64);
   // measured on B200 (tools/perf_probe.py eocfg): the 1 x 4 warp layout (half as many E/O adds per
   // DMMA) is 1-6 % faster than 2 x 2
-  const int cfg = g_eo_config >= 0 ? g_eo_config : (ctas < pt::sm_count() ? 1 : 2);
+  // half-rows that split into <= 6 row-tiles per tile (n = 257: 17 row-tiles = 6 + 6 + 5) fit the
+  // 48-row tile with 3 CTAs/SM better than the 64-row one (measured 0.206 vs 0.222 ms)
+  const int rtiles = (p.H + 7) / 8, mb = (rtiles + 7) / 8, rt_bal = (rtiles + mb - 1) / mb;
+  const int cfg = g_eo_config >= 0 ? g_eo_config : (ctas < pt::sm_count() ? 1 : (rt_bal <= 6 ? 3 : 2));
   if (cfg == 1) return launch_eo<2, 2, 2, 2, 4, 3, KCONTIG, VEC16, 4, SCAT>(p, stream);   // 32 half-rows x 32 columns
   if (cfg == 2) return launch_eo<1, 4, 8, 2, 4, 3, KCONTIG, VEC16, 2, SCAT>(p, stream);   // 64 x 64, warps side by side
+  if (cfg == 3) return launch_eo<1, 4, 6, 2, 2, 3, KCONTIG, VEC16, 3, SCAT>(p, stream);   // 48 x 64, 3 CTAs/SM, 8-wide k chunks
   return launch_eo<2, 2, 4, 4, 4, 3, KCONTIG, VEC16, 2, SCAT>(p, stream);                 // 64 half-rows x 64 columns
 }
 

@@ -56,18 +56,18 @@ def test_eo_matches_oracle_on_symmetrised_random_operators(n, sign):
             ref = alpha * oracle.apply_along_axis(D, U[None], npts, 1)[0] + beta * Y0
             bound = abs(alpha) * oracle.abs_bound(D, U[None], npts, 1)[0] + abs(beta) * np.abs(Y0)
             assert np.max(np.abs(got - ref) / bound) <= TOL, (n, sign, before, after, alpha)
-    # both tile shapes give the same bits
+    # every tile shape gives the same bits
     lib = _lib.load()
     op = _DiffMat._wrap(d_D, (6, n, 5), 1, 2 if sign == 1 else 1, None)
     U = torch.from_numpy(rng.standard_normal(6 * n * 5)).cuda()
     res = []
     try:
-        for cfg in (0, 1):
+        for cfg in (0, 1, 2, 3):
             lib.pt_debug_set_eo_config(cfg)
             res.append(op.apply(U))
     finally:
         lib.pt_debug_set_eo_config(-1)
-    assert torch.equal(res[0], res[1])
+    assert all(torch.equal(res[0], r) for r in res[1:])
 
 
 @pytest.mark.gpu
