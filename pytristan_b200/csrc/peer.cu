@@ -62,8 +62,11 @@ struct ScatterCopyParams {
 
 // One thread per V doubles of a contiguous run.  before > 1: a run is the `before` contiguous
 // doubles of one (a, i); before == 1 (and s_i == 1): a run is the `chunk` rows that go to one rank.
+// 128-thread CTAs at <= 40 registers: small enough to share an SM with two resident CTAs of the
+// even-odd DMMA kernel (224 registers x 128 threads each), so the redistribution of the field
+// really runs UNDER the operator kernel of the other stream instead of after it
 template <int V>
-__global__ void __launch_bounds__(256) peer_scatter_kernel(const ScatterCopyParams p, int64_t run_len,
+__global__ void __launch_bounds__(128) peer_scatter_kernel(const ScatterCopyParams p, int64_t run_len,
                                                             int64_t total) {
   const int64_t per_run = run_len / V;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
@@ -165,10 +168,10 @@ extern "C" int pt_peer_scatter(const double* src, int n, int64_t after, int64_t 
                     (before > 1 ? !(map->s_i & 1) : (n % 2 == 0));
   const bool vec = even && aligned16(src);
   const int64_t total = runs * (run_len / (vec ? 2 : 1));
-  int64_t blocks = (total + 255) / 256;
+  int64_t blocks = (total + 127) / 128;
   const int64_t cap = int64_t(pt::sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  if (vec) peer_scatter_kernel<2><<<unsigned(blocks), 256, 0, pt::as_stream(stream)>>>(p, run_len, total);
-  else peer_scatter_kernel<1><<<unsigned(blocks), 256, 0, pt::as_stream(stream)>>>(p, run_len, total);
+  if (vec) peer_scatter_kernel<2><<<unsigned(blocks), 128, 0, pt::as_stream(stream)>>>(p, run_len, total);
+  else peer_scatter_kernel<1><<<unsigned(blocks), 128, 0, pt::as_stream(stream)>>>(p, run_len, total);
   return pt::check_launch("pt_peer_scatter");
 }
