@@ -48,7 +48,12 @@ struct EoCfg {
   static constexpr int BN = WARPS_N * WN * 8;
   static constexpr int BK = BKP * 4;
   static constexpr int A_STAGE = BKP * 2 * BMH * 4;                 // per panel PAIR: [even rows][odd rows] x 8
-  static constexpr int PB = KCONTIG ? (BK + 4) : (BN + 4);
+  // field tile pitch.  K1 ([k][column], 8-byte fragment reads of rows 2t and 2t+1): BN + 2 puts the
+  // 16 lanes of a half-warp in 16 different banks.  K2 ([column][k], 16-byte fragment reads): no
+  // padding; for 16-wide k chunks the 16-byte pieces of odd columns are stored XOR 4 (swizzle), so
+  // that the 8 lanes of a quarter-warp (2 columns x 4 pieces) cover all 8 bank groups.
+  static constexpr int PB = KCONTIG ? BK : (BN + 2);
+  static constexpr int SWZ = (KCONTIG && BK == 16) ? 4 : 0;     // piece-index XOR of odd columns
   static constexpr int B_TILE = KCONTIG ? BN * PB : BK * PB;
   static constexpr int STAGE = A_STAGE + 2 * B_TILE;                // field tile + mirrored field tile
   static constexpr size_t SMEM = size_t(STAGES) * STAGE * sizeof(double);
@@ -59,7 +64,7 @@ struct EoCfg {
 // the first panel takes k = 8P + 2t, the second k = 8P + 2t + 1 (any split of the 8 k into two
 // groups of 4 is a valid pair of DMMA k-panels); the field fragments follow the same assignment.
 template <class C, int RT, int WR, int WN, bool KCONTIG, bool VEC16>
-__device__ __forceinline__ void eo_frags(const double* As, const double* B1, const double* B2, int pr,
+__device__ __forceinline__ void eo_frags(const double* As, const double* B1, const double* B2, int pr, int swz,
                                          double2 (&ae)[WR], double2 (&ao)[WR], double2 (&be)[WN], double2 (&bo)[WN]) {
 #pragma unroll
   for (int i = 0; i < RT; ++i) {
@@ -70,8 +75,9 @@ __device__ __forceinline__ void eo_frags(const double* As, const double* B1, con
   for (int j = 0; j < WN; ++j) {
     double f1a, f1b, f2a, f2b;     // a: k = 8P + 2t, b: k = 8P + 2t + 1 (B1/B2 already hold the lane's 2t offset)
     if (KCONTIG) {
-      const double2 v1 = *reinterpret_cast<const double2*>(B1 + j * 8 * C::PB + pr * 8);
-      const double2 v2 = *reinterpret_cast<const double2*>(B2 + j * 8 * C::PB + pr * 8);
+      // swz = 1 for the odd columns of a swizzled tile: their pieces 0-3 and 4-7 are exchanged
+      const double2 v1 = *reinterpret_cast<const double2*>(B1 + j * 8 * C::PB + (pr ^ swz) * 8);
+      const double2 v2 = *reinterpret_cast<const double2*>(B2 + j * 8 * C::PB + (pr ^ swz) * 8);
       f1a = v1.x; f1b = v1.y;
       // mirrored tile: 16-byte copies keep the memory order inside a pair, i.e. the pair is swapped
       if (VEC16) { f2a = v2.y; f2b = v2.x; } else { f2a = v2.x; f2b = v2.y; }
@@ -85,14 +91,14 @@ __device__ __forceinline__ void eo_frags(const double* As, const double* B1, con
 }
 
 template <class C, int RT, int WR, int WN, int BKP, bool KCONTIG, bool VEC16>
-__device__ __forceinline__ void eo_compute(const double* As, const double* B1, const double* B2, int npairs,
+__device__ __forceinline__ void eo_compute(const double* As, const double* B1, const double* B2, int npairs, int swz,
                                            double (&acce)[WR][WN][2], double (&acco)[WR][WN][2]) {
   static_assert(BKP % 2 == 0, "k-panels are processed in pairs");
   if (npairs == BKP / 2) {
 #pragma unroll
     for (int pr = 0; pr < BKP / 2; ++pr) {
       double2 ae[WR], ao[WR], be[WN], bo[WN];
-      eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pr, ae, ao, be, bo);
+      eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pr, swz, ae, ao, be, bo);
       // consecutive DMMAs share their A operand (operand reuse), as in the plain kernel
 #pragma unroll
       for (int i = 0; i < RT; ++i) {
@@ -113,7 +119,7 @@ __device__ __forceinline__ void eo_compute(const double* As, const double* B1, c
 #pragma unroll 1
     for (int pr = 0; pr < npairs; ++pr) {
       double2 ae[WR], ao[WR], be[WN], bo[WN];
-      eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pr, ae, ao, be, bo);
+      eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pr, swz, ae, ao, be, bo);
 #pragma unroll
       for (int i = 0; i < RT; ++i)
 #pragma unroll
@@ -131,14 +137,14 @@ __device__ __forceinline__ void eo_compute(const double* As, const double* B1, c
 template <class C, int RT, int WR, int WN, int BKP, bool KCONTIG, bool VEC16>
 struct EoDispatch {
   static __device__ __forceinline__ void run(int my_rt, const double* As, const double* B1, const double* B2,
-                                             int npairs, double (&acce)[WR][WN][2], double (&acco)[WR][WN][2]) {
-    if (my_rt == RT) eo_compute<C, RT, WR, WN, BKP, KCONTIG, VEC16>(As, B1, B2, npairs, acce, acco);
-    else EoDispatch<C, RT - 1, WR, WN, BKP, KCONTIG, VEC16>::run(my_rt, As, B1, B2, npairs, acce, acco);
+                                             int npairs, int swz, double (&acce)[WR][WN][2], double (&acco)[WR][WN][2]) {
+    if (my_rt == RT) eo_compute<C, RT, WR, WN, BKP, KCONTIG, VEC16>(As, B1, B2, npairs, swz, acce, acco);
+    else EoDispatch<C, RT - 1, WR, WN, BKP, KCONTIG, VEC16>::run(my_rt, As, B1, B2, npairs, swz, acce, acco);
   }
 };
 template <class C, int WR, int WN, int BKP, bool KCONTIG, bool VEC16>
 struct EoDispatch<C, 0, WR, WN, BKP, KCONTIG, VEC16> {
-  static __device__ __forceinline__ void run(int, const double*, const double*, const double*, int,
+  static __device__ __forceinline__ void run(int, const double*, const double*, const double*, int, int,
                                              double (&)[WR][WN][2], double (&)[WR][WN][2]) {}
 };
 
@@ -158,6 +164,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
   constexpr int CPR2 = C::BK / EPC, RPP2 = C::NT / CPR2;            // K2: chunks per column, columns per pass
   static_assert(KCONTIG || (C::NT % CPR1 == 0 && C::BK % RPP1 == 0), "K1 loader shape");
   static_assert(!KCONTIG || (C::NT % CPR2 == 0 && C::BN % RPP2 == 0), "K2 loader shape");
+  static_assert(!KCONTIG || RPP2 % 2 == 0, "the swizzle of a thread's columns must not depend on the pass");
   constexpr int APIECES = C::BMH * 4;                                // 16-byte pieces of one panel-PAIR half (8 doubles per row)
   constexpr int ASUB = (APIECES + C::NT - 1) / C::NT;
   const int b_cc = KCONTIG ? tid % CPR2 : tid % CPR1;
@@ -261,8 +268,10 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
         // the piece k .. k+EPC-1 and its mirror n-EPC-k .. n-1-k lie inside the row iff k+EPC <= n
         const bool ok = (nn < p.NN) && (k + EPC <= n);
         const double* row = p.U + nn * n;
-        double* d1 = B1 + col * C::PB + b_cc * EPC;
-        double* d2 = B2 + col * C::PB + b_cc * EPC;
+        const int sw = (col & 1) ? C::SWZ : 0;
+        const int slot = VEC16 ? ((b_cc ^ sw) * 2) : ((((b_cc >> 1) ^ sw) << 1) | (b_cc & 1));
+        double* d1 = B1 + col * C::PB + slot;
+        double* d2 = B2 + col * C::PB + slot;
         if (VEC16) {
           cp_async16(d1, ok ? row + k : p.U, ok ? 16 : 0);
           cp_async16(d2, ok ? row + (n - 2 - k) : p.U, ok ? 16 : 0);
@@ -299,7 +308,11 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
 #pragma unroll
     for (int r = 0; r < BR; ++r) {
       const bool ok = (b_ok >> (KCONTIG ? r : 0)) & 1u;
-      const int so = (b_r0 + r * RPP) * C::PB + b_cc * EPC;
+      int so = (b_r0 + r * RPP) * C::PB + b_cc * EPC;
+      if (KCONTIG && C::SWZ) {          // column parity is constant over r (RPP is even)
+        const int sw = (b_r0 & 1) ? C::SWZ : 0;
+        so = (b_r0 + r * RPP) * C::PB + (VEC16 ? ((b_cc ^ sw) * 2) : ((((b_cc >> 1) ^ sw) << 1) | (b_cc & 1)));
+      }
       const double* s1 = ok ? b1_ptr + r * b_rstep : p.U;
       const double* s2 = ok ? (KCONTIG ? b2_ptr + r * b_rstep : b2_ptr - r * b_rstep) : p.U;
       if (VEC16) { cp_async16(B1 + so, s1, ok ? 16 : 0); cp_async16(B2 + so, s2, ok ? 16 : 0); }
@@ -332,6 +345,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
   // (the pair swap of the mirrored tile is undone when the fragments are read, eo_frags)
   const int b1_off = KCONTIG ? ((wn * WN * 8 + g) * C::PB + 2 * t) : (2 * t * C::PB + wn * WN * 8 + g);
   const int b2_off = b1_off;
+  const int frag_swz = (C::SWZ && (g & 1)) ? 1 : 0;   // odd columns of a swizzled tile: pair index XOR 1
   const int nfull = p.KPH / BKP;
   const int tail = (p.KPH - nfull * BKP) / 2;        // panel pairs of the last, partial chunk
   const bool use_beta = (p.beta != 0.0);
@@ -365,7 +379,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
       const double* B2 = B1 + C::B_TILE;
       ++consumed;
       EoDispatch<C, WR, WR, WN, BKP, KCONTIG, VEC16>::run(my_rt, As + a_off, B1 + b1_off, B2 + b2_off,
-                                                          kc < nfull ? BKP / 2 : tail, acce, acco);
+                                                          kc < nfull ? BKP / 2 : tail, frag_swz, acce, acco);
     }
 
     // ---- epilogue: rows i (ze + zo) and n-1-i (s*(ze - zo)) --------------------------------------------
