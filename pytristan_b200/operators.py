@@ -11,7 +11,10 @@ whose entries were generated on the GPU (``pt_gen_chebmat`` / ``pt_gen_fourmat``
 ``pt_gen_fornberg``) and which keeps device-resident forms for application:
 
 * dense operators keep the fragment-major packed copy read by the FP64 tensor-core kernels
-  (``pt_dense_apply``: K1 for a strided axis, K2 for axis 0);
+  (``pt_dense_apply``: K1 for a strided axis, K2 for axis 0); operators that are
+  centro(anti)symmetric — every ``FourMat``, every ``ChebMat`` on a CGL axis — keep the two packed
+  half-size operators of the even-odd decomposition instead and are applied with half the
+  tensor-core work (``pt_dense_apply_eo``; decided once per operator by ``pt_operator_symmetry``);
 * ``FinDiffMat`` keeps the banded row-start form read by the stencil kernels
   (``pt_stencil_apply``: K3/K4).
 
