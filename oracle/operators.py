@@ -73,6 +73,17 @@ def _seq_row_sum(M):
     return np.cumsum(M, axis=1)[:, -1]
 
 
+def nodes_symmetric(x):
+    """True when the nodes are symmetric about their midpoint to within 8 ulp of their span (every
+    affine CGL set; stretched meshes whose mapper is odd about the centre)."""
+    x = np.asarray(x, dtype=np.float64)
+    if x.size < 2:
+        return False
+    c2 = x[0] + x[-1]
+    scale = max(float(np.max(np.abs(x))), abs(float(x[-1] - x[0])))
+    return bool(np.max(np.abs(x + x[::-1] - c2)) <= 8.0 * np.finfo(np.float64).eps * scale)
+
+
 def flip_symmetrize(D, sign):
     """Flipping trick (Don & Solomonoff 1995): rows below the middle, and the right part of the
     middle row of an odd n, become the mirror image of the rows above, D[i,j] = sign*D[n-1-i,n-1-j]
@@ -88,7 +99,7 @@ def flip_symmetrize(D, sign):
     return D
 
 
-def cheb_mat(x, order=1, flip=True):
+def cheb_mat(x, order=1, flip=None):
     """Collocation differentiation matrix of ``order`` on nodes ``x`` (any affine image of the
     CGL set, either orientation).  With ``flip`` (default, what ChebMat generates) the lower half
     is the mirror image of the upper half, so the matrix is exactly centro(anti)symmetric.
@@ -113,10 +124,12 @@ def cheb_mat(x, order=1, flip=True):
         Dn = np.where(off, (l / dx) * (cr * diag[:, None] - D), 0.0)
         Dn[~off] = -_seq_row_sum(Dn)
         D = Dn
+    if flip is None:
+        flip = nodes_symmetric(x)       # every affine CGL set is symmetric about its midpoint
     return flip_symmetrize(D, 1 if order % 2 == 0 else -1) if flip else D
 
 
-def bary_mat(x, order=1):
+def bary_mat(x, order=1, flip=None):
     """Polynomial collocation differentiation matrix on ARBITRARY distinct nodes (what a
     non-affine mapper of the reference produces, grid.py:201-207): barycentric weights
     w_j = 1/prod_{k!=j}(x_j-x_k) (Berrut & Trefethen 2004), D1_ij = (w_j/w_i)/(x_i-x_j), higher
@@ -141,7 +154,9 @@ def bary_mat(x, order=1):
         Dn = np.where(off, (l / dx) * (cr * diag[:, None] - D), 0.0)
         Dn[~off] = -_seq_row_sum(Dn)
         D = Dn
-    return D
+    if flip is None:
+        flip = nodes_symmetric(x)       # same rule as ChebMat: symmetric nodes -> flipping trick
+    return flip_symmetrize(D, 1 if order % 2 == 0 else -1) if flip else D
 
 
 def is_affine_cgl(x, tol=1e-13):

@@ -80,6 +80,16 @@ def _resolve_axis(grid, axis):
     return nodes, (nodes.size,), 0, None
 
 
+def _nodes_symmetric(x):
+    """Nodes symmetric about their midpoint to within 8 ulp of their span (oracle: nodes_symmetric)."""
+    x = np.asarray(x, dtype=np.float64)
+    if x.size < 2:
+        return False
+    c2 = x[0] + x[-1]
+    scale = max(float(np.max(np.abs(x))), abs(float(x[-1] - x[0])))
+    return bool(np.max(np.abs(x + x[::-1] - c2)) <= 8.0 * np.finfo(np.float64).eps * scale)
+
+
 def _is_uniform(x):
     n = x.size
     if n < 3:
@@ -401,14 +411,17 @@ class ChebMat(_DiffMat):
         if weights == "cgl":
             _lib.check(lib.pt_gen_chebmat(_lib.dptr(d_x), n, order, _lib.dptr(d_mat),
                                           _lib.stream_ptr()), "pt_gen_chebmat")
-            # flipping trick: exactly centro(anti)symmetric on the symmetric CGL set
-            _lib.check(lib.pt_flip_symmetrize(_lib.dptr(d_mat), n, 1 if order % 2 == 0 else -1,
-                                              _lib.stream_ptr()), "pt_flip_symmetrize")
         else:
             # nodes from a non-affine mapper: polynomial collocation with barycentric weights
             work = _lib.empty((2 * n,))
             _lib.check(lib.pt_gen_barymat(_lib.dptr(d_x), n, order, _lib.dptr(d_mat), _lib.dptr(work),
                                           _lib.stream_ptr()), "pt_gen_barymat")
+        if _nodes_symmetric(nodes):
+            # flipping trick on node sets that are symmetric about their midpoint (every affine CGL
+            # set; stretched meshes with an odd mapper): exactly centro(anti)symmetric matrix, which
+            # the even-odd kernel applies with half the tensor-core work
+            _lib.check(lib.pt_flip_symmetrize(_lib.dptr(d_mat), n, 1 if order % 2 == 0 else -1,
+                                              _lib.stream_ptr()), "pt_flip_symmetrize")
         obj = cls._wrap(d_mat, npts, axis, order, gnum)
         obj.weights_kind = weights
         return obj

@@ -123,6 +123,19 @@ def test_real_operators_take_the_even_odd_path_and_agree_with_the_plain_kernel()
     x = oracle.cheb_nodes(40)[::-1]
     stretched = pt.ChebMat(x + 0.15 * (1.0 - x * x), order=1)
     assert stretched._eo_forms() is None
+    # a stretching mapper that is odd about the centre keeps the node set symmetric: the barycentric
+    # matrix is flipped like the CGL one and takes the even-odd path
+    xs = np.sinh(2.0 * x) / np.sinh(2.0)
+    assert oracle.nodes_symmetric(xs) and not oracle.is_affine_cgl(xs)
+    for order in (1, 2):
+        op = pt.ChebMat(xs, order=order)
+        assert op.weights_kind == "bary" and op._eo_forms() is not None
+        ref = oracle.bary_mat(xs, order)
+        assert np.max(np.abs(np.asarray(op) - ref) / np.abs(ref).sum(axis=1, keepdims=True)) <= 1e-13
+        op.npts, op.axis = (40, 9), 0
+        U = rng.standard_normal((2, 360))
+        got = op.apply(torch.from_numpy(U).cuda()).cpu().numpy()
+        assert np.max(np.abs(got - oracle.apply_along_axis(ref, U, (40, 9), 0)) / oracle.abs_bound(ref, U, (40, 9), 0)) <= TOL
 
 
 @pytest.mark.gpu
