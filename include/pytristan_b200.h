@@ -4,7 +4,7 @@
  * Drop-in boundary.  The reference (pytristan 0.2a) is pure Python/NumPy and
  * has no FFI; every entry point below replaces a NumPy call site of the reference or the
  * operator layer its README announces (README.md:7-10,16,24-26).  The Python façade
- * (pytristan_b200/*.py) binds these with ctypes; INTEGRATION.md shows the stub a reference
+ * (the modules under pytristan_b200/) binds these with ctypes; INTEGRATION.md shows the stub a reference
  * maintainer would add.
  *
  * Conventions
