@@ -245,7 +245,7 @@ def run_reference(args, spec):
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -440,7 +440,7 @@ def run_gpu(args, spec):
         "gpu_launches": args.steps * pt.launches_per_apply(ops) * world,
         "clocks": sampler.summary(),
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -591,7 +591,7 @@ def run_gpu_sharded(args, spec):
                            "l2": "per-rank field larger than L2" if host_bytes > 126e6 else "per-rank field fits L2 (strong scaling)"},
                 "roofline": roof, "cpu_baseline": None,
                 "e2e": None, "gpu_launches": args.steps * launches * world, "clocks": sampler.summary()}
-        print(json.dumps(line))
+        emit(line)
     if fab is not None:
         fab.check()
         fab.close()
@@ -599,7 +599,31 @@ def run_gpu_sharded(args, spec):
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def reserve_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's
+    back (NCCL prints its version banner there when the first communicator is created), so the
+    descriptor is pointed at stderr for the whole run and the line goes to the saved original."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
