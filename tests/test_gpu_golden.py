@@ -156,3 +156,39 @@ def test_device_grid_config4_size():
     assert torch.equal(t[1].view(n, n, n)[3, :, 9], 2.0 * tx)
     assert torch.equal(t[2].view(n, n, n)[:, 11, 2], -tx)
     assert float(t[0].sum()) == pytest.approx(float(x.sum()) * n * n, rel=1e-12)
+
+
+def test_operator_generators_against_the_frozen_known_answers():
+    """Device generators vs tests/golden/operator_kat.npz (frozen oracle outputs): the stencil index
+    layout and the off-diagonal Chebyshev entries bit for bit, every entry within 1e-13 of its
+    row's absolute sum."""
+    import pytristan_b200 as pt
+
+    kat = np.load(os.path.join(GOLDEN_DIR, "operator_kat.npz"))
+
+    def close(got, ref, tol=1e-13):
+        scale = np.abs(ref).sum(axis=1, keepdims=True)
+        return np.max(np.abs(np.asarray(got) - ref) / np.where(scale > 0, scale, 1.0)) <= tol
+
+    for n in (8, 9, 33):
+        x = kat[f"cheb_nodes_{n}"]
+        for order in (1, 2, 3):
+            ref = kat[f"cheb_mat_{n}_o{order}"]
+            D = np.asarray(pt.ChebMat(x, order=order))
+            assert close(D, ref)
+            if order == 1:
+                off = ~np.eye(n, dtype=bool)
+                assert np.array_equal(D[off], ref[off])
+    assert close(pt.ChebMat(kat["bary_nodes_17"], order=2), kat["bary_mat_17_o2"])
+    for n in (8, 9, 32):
+        x = np.arange(n) * (2 * np.pi / n)
+        for order in (1, 2, 3, 4):
+            assert close(pt.FourMat(x, order=order), kat[f"four_mat_{n}_o{order}"], 1e-12 if order > 2 else 1e-13)
+    cases = {"uni": (np.linspace(0.0, 1.0, 21), False), "per": (np.linspace(0.0, 1.0 - 1.0 / 20, 20), True)}
+    from oracle import operators as oracle
+    cases["map"] = (oracle.cheb_nodes(21, 0.0, 1.0), False)
+    for tag, (x, periodic) in cases.items():
+        for (order, acc) in ((1, 2), (1, 6), (2, 4)):
+            F = pt.FinDiffMat(x, order=order, accuracy=acc, periodic=periodic)
+            assert np.array_equal(np.asarray(F.start, dtype=np.int64), kat[f"fd_{tag}_o{order}a{acc}_start"])
+            assert close(F.weights, kat[f"fd_{tag}_o{order}a{acc}_W"])

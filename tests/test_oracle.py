@@ -237,3 +237,21 @@ def test_four_general_vs_fft_and_closed_forms(n, order):
     spec = np.real(np.fft.ifft((1j * k) ** order * np.fft.fft(f)))
     D = oracle.four_mat(n, period, order) if order > 2 else col[(np.arange(n)[:, None] - np.arange(n)[None, :]) % n]
     assert np.max(np.abs(D @ f - spec)) <= 1e-11 * np.abs(D).sum(axis=1).max() * np.max(np.abs(f))
+
+
+def test_operator_known_answer_vectors_are_stable():
+    """The oracle's operator conventions, frozen in tests/golden/operator_kat.npz by
+    tests/golden/make_operator_kat.py: any drift (summation order, flipping rule, band layout)
+    shows up here bit for bit."""
+    import importlib.util
+    import os
+
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_operator_kat", os.path.join(here, "make_operator_kat.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.build()
+    frozen = np.load(os.path.join(here, "operator_kat.npz"))
+    assert sorted(frozen.files) == sorted(now)
+    for key in frozen.files:
+        assert frozen[key].dtype == now[key].dtype and np.array_equal(frozen[key], now[key]), key
