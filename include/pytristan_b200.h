@@ -140,8 +140,9 @@ int pt_dense_apply(const double* packed, int n_out, int n_in, const double* U, d
 
 /* ---- K1/K2 for centrosymmetric operators: even-odd decomposition (half the tensor-core work) ---- */
 /* Largest entrywise violation of J D J = sign * D (J = order reversal), relative to the entry:
- * 0 for an exactly centro(anti)symmetric matrix.  Written to *worst_host (synchronises). */
-int pt_operator_symmetry(const double* D, int n, int sign, double* worst_host, pt_stream_t stream);
+ * 0 for an exactly centro(anti)symmetric matrix.  Written to the caller-owned DEVICE scalar
+ * *worst_dev in stream order (nothing is allocated, nothing synchronises). */
+int pt_operator_symmetry(const double* D, int n, int sign, double* worst_dev, pt_stream_t stream);
 /* Doubles of each of the two packed half operators. */
 int64_t pt_packed_eo_size(int n);
 /* Ae[i][k] = (D[i][k] + D[i][n-1-k])/2 and Ao[i][k] = (D[i][k] - D[i][n-1-k])/2 for i, k < ceil(n/2)

@@ -80,7 +80,7 @@ SIGNATURES = {
     "pt_dense_apply": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64,
                                 _c_f64, _c_ptr, _c_i32, _c_i64, _c_ptr]),
     "pt_flip_symmetrize": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr]),
-    "pt_operator_symmetry": (_c_i32, [_c_ptr, _c_i32, _c_i32, ctypes.POINTER(_c_f64), _c_ptr]),
+    "pt_operator_symmetry": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr]),
     "pt_packed_eo_size": (_c_i64, [_c_i32]),
     "pt_operator_pack_eo": (_c_i32, [_c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
     "pt_dense_apply_eo": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64, _c_f64,
@@ -220,6 +220,8 @@ def to_device(arr, dtype=None):
     caller's business)."""
     torch = require_cuda()
     a = np.ascontiguousarray(arr, dtype=dtype)
+    if not a.flags.writeable:
+        a = np.array(a)           # torch.from_numpy refuses to alias read-only memory silently
     return torch.from_numpy(a).cuda(non_blocking=False)
 
 

@@ -591,25 +591,18 @@ extern "C" int64_t pt_packed_eo_size(int n) {
   return ((H + 7) / 8) * (8 * ((H + 7) / 8)) * 8;
 }
 
-extern "C" int pt_operator_symmetry(const double* D, int n, int sign, double* worst_host, pt_stream_t stream) {
-  PT_REQUIRE(D && worst_host, "pt_operator_symmetry: null pointer");
+extern "C" int pt_operator_symmetry(const double* D, int n, int sign, double* worst_dev, pt_stream_t stream) {
+  PT_REQUIRE(D && worst_dev, "pt_operator_symmetry: null pointer");
   PT_REQUIRE(n >= 1 && (sign == 1 || sign == -1), "pt_operator_symmetry: bad argument");
+  // stream-ordered, nothing allocated, no synchronisation: the caller owns the device scalar (the
+  // bit pattern of a non-negative double orders like the unsigned integer the kernel takes the
+  // maximum of) and reads it back when it wants the verdict
   cudaStream_t st = pt::as_stream(stream);
-  unsigned long long* d_w = nullptr;
-  PT_CUDA(cudaMalloc(&d_w, sizeof(unsigned long long)));
-  PT_CUDA(cudaMemsetAsync(d_w, 0, sizeof(unsigned long long), st));
+  PT_CUDA(cudaMemsetAsync(worst_dev, 0, sizeof(double), st));
   int64_t blocks = (int64_t(n) * n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  symmetry_kernel<<<unsigned(blocks), 256, 0, st>>>(D, n, sign, d_w);
-  unsigned long long bits = 0;
-  cudaError_t e = cudaMemcpyAsync(&bits, d_w, sizeof(bits), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(d_w);
-  if (e != cudaSuccess) return pt::fail(PT_ERR_CUDA, "pt_operator_symmetry: %s", cudaGetErrorString(e));
-  double w;
-  memcpy(&w, &bits, sizeof(w));
-  *worst_host = w;
-  return PT_OK;
+  symmetry_kernel<<<unsigned(blocks), 256, 0, st>>>(D, n, sign, reinterpret_cast<unsigned long long*>(worst_dev));
+  return pt::check_launch("pt_operator_symmetry");
 }
 
 extern "C" int pt_operator_pack_eo(const double* D, int n, double* packed_even, double* packed_odd,

@@ -123,24 +123,17 @@ def _expand_axes(axes, dtype):
     return out
 
 
-def _expand_axes_device(axes, dtype):
-    """Axis arrays -> ``(ndim, prod(npts))`` CUDA tensor in the Grid layout (no host copy)."""
+def _expand_device_axes(d_axes, npts, dtype):
+    """Concatenated axis arrays ALREADY on the device -> ``(ndim, prod(npts))`` CUDA tensor."""
     torch = _lib.require_cuda()
     lib = _lib.load()
-    tdtype = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
-              np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32}.get(np.dtype(dtype))
-    if tdtype is None:
-        raise TypeError(f"DeviceGrid: unsupported coordinate dtype {dtype}")
-    ndim = len(axes)
-    npts = [int(a.shape[0]) for a in axes]
+    ndim = len(npts)
     total = 1
     for n in npts:
-        total *= n
-    out = torch.empty((ndim, total), dtype=tdtype, device="cuda")
+        total *= int(n)
+    out = torch.empty((ndim, total), dtype=d_axes.dtype, device="cuda")
     if total:
-        flat = np.concatenate([np.ascontiguousarray(a, dtype=dtype) for a in axes])
-        d_axes = torch.from_numpy(flat).cuda()
-        c_npts = (ctypes.c_int64 * ndim)(*npts)
+        c_npts = (ctypes.c_int64 * ndim)(*[int(n) for n in npts])
         _lib.check(
             lib.pt_grid_expand(_lib.dptr(d_axes), c_npts, ndim, np.dtype(dtype).itemsize, _lib.dptr(out),
                                _lib.stream_ptr()),
@@ -149,21 +142,69 @@ def _expand_axes_device(axes, dtype):
     return out
 
 
+def _expand_axes_device(axes, dtype):
+    """Host axis arrays -> ``(ndim, prod(npts))`` CUDA tensor in the Grid layout (no host copy)."""
+    torch = _lib.require_cuda()
+    tdtype = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
+              np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32}.get(np.dtype(dtype))
+    if tdtype is None:
+        raise TypeError(f"DeviceGrid: unsupported coordinate dtype {dtype}")
+    npts = [int(a.shape[0]) for a in axes]
+    flat = np.concatenate([np.ascontiguousarray(a, dtype=dtype) for a in axes])
+    if flat.size == 0:
+        return torch.empty((len(axes), 0), dtype=tdtype, device="cuda")
+    return _expand_device_axes(torch.from_numpy(flat).cuda(), npts, dtype)
+
+
+def _linspace_device(start, stop, num):
+    """``numpy.linspace(start, stop, num)`` evaluated on the GPU (``pt_gen_linspace``: the same
+    ``fl(fl(i*step)+start)`` arithmetic with explicit rounding, last node overwritten with ``stop``),
+    bit-identical to NumPy's for float64 bounds."""
+    torch = _lib.require_cuda()
+    try:
+        n = operator.index(num)
+    except TypeError as exc:
+        raise TypeError(f"object of type {type(num)} cannot be safely interpreted as an integer.") from exc
+    if n < 0:
+        raise ValueError(f"Number of samples, {n}, must be non-negative.")
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().pt_gen_linspace(_lib.dptr(x), float(start), float(stop), n, _lib.stream_ptr()),
+               "pt_gen_linspace")
+    return x
+
+
 class DeviceGrid:
     """Device-resident mesh with the Grid layout: ``tensor`` is a CUDA
     ``(ndim, prod(npts))`` array with the same values, bit for bit, as ``Grid`` would hold, but it
     is never copied to the host — this is how meshes the reference cannot materialise on a host
     (1024^3: 24 GiB, ~72 GiB peak in reference grid.py:83-88) are built in milliseconds.
 
+    ``from_bounds`` generates the 1-D nodes on the device as well: ``pt_gen_linspace`` for unmapped
+    axes and ``cheb_device`` (``pt_gen_cheb_libm``, the host libm's cosine bit for bit) for axes
+    mapped with ``cheb``; other mappers are called on the host as the reference does
+    (grid.py:201-207).  ``axpoints`` is the strided read of a grid row (``pt_grid_axpoints``,
+    reference grid.py:277-280) brought to the host.
+
     Same constructors and accessors as ``Grid`` (``from_bounds``, ``from_arrs``, ``axpoints``,
     ``npts``, ``num_dim``, ``num``); operators accept it wherever they accept a ``Grid``.
     """
 
     def __init__(self, arrs):
-        axes = [np.asarray(a).ravel() for a in arrs]
-        if not axes:
+        torch = _lib.require_cuda()
+        arrs = list(arrs)
+        if not arrs:
             raise ValueError("DeviceGrid needs at least one axis")
-        self._axes = [np.array(a) for a in axes]
+        if any(isinstance(a, torch.Tensor) for a in arrs):
+            # axes generated on the device (from_bounds): float64 nodes, never copied to the host
+            d_axes = [a.to(device="cuda", dtype=torch.float64).reshape(-1) if isinstance(a, torch.Tensor)
+                      else torch.from_numpy(np.ascontiguousarray(np.asarray(a).ravel(), dtype=np.float64)).cuda()
+                      for a in arrs]
+            self.npts = tuple(int(a.numel()) for a in d_axes)
+            self.num_dim = len(d_axes)
+            self._num = None
+            self.tensor = _expand_device_axes(torch.cat(d_axes), self.npts, np.dtype(np.float64))
+            return
+        axes = [np.asarray(a).ravel() for a in arrs]
         self.npts = tuple(len(a) for a in axes)
         self.num_dim = len(axes)
         self._num = None
@@ -171,7 +212,7 @@ class DeviceGrid:
 
     @classmethod
     def from_bounds(cls, *bounds, axes=[], mappers=[]):
-        return cls(Grid._axes_from_bounds(bounds, axes, mappers))
+        return cls(Grid._axes_from_bounds(bounds, axes, mappers, device=True))
 
     @classmethod
     def from_arrs(cls, *arrs):
@@ -188,18 +229,34 @@ class DeviceGrid:
     def shape(self):
         return tuple(self.tensor.shape)
 
-    def axpoints(self, axis):
+    def axpoints_device(self, axis):
+        """1-D nodes of ``axis`` as a CUDA tensor: strided gather of row ``axis`` of the grid
+        (``pt_grid_axpoints``; float64 grids)."""
+        torch = _lib.require_cuda()
         try:
             operator.index(axis)
         except TypeError as exc:
             raise TypeError("Axis' index axis must be an integer.") from exc
         if axis >= self.num_dim or axis < -self.num_dim:
             raise IndexError(f"Axis' index {axis} out of bounds for the grid with {self.num_dim} dimensions.")
-        return np.array(self._axes[axis])
+        axis = axis + self.num_dim if axis < 0 else axis
+        stride = 1
+        for n in self.npts[:axis]:
+            stride *= n
+        n = self.npts[axis]
+        if self.tensor.dtype != torch.float64:
+            return self.tensor[axis, :stride * n:stride].contiguous()
+        x = torch.empty(n, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.load().pt_grid_axpoints(_lib.dptr(self.tensor[axis]), stride, n, _lib.dptr(x),
+                                                _lib.stream_ptr()), "pt_grid_axpoints")
+        return x
+
+    def axpoints(self, axis):
+        return self.axpoints_device(axis).cpu().numpy()
 
     def to_host(self):
         """The equivalent host ``Grid`` (copies ``ndim * prod(npts)`` elements)."""
-        return Grid(self._axes)
+        return Grid([self.axpoints(k) for k in range(self.num_dim)])
 
     def __repr__(self):
         tag = "no unique identifier" if self._num is None else f"unique identifier: {self._num}"
@@ -240,7 +297,7 @@ class Grid(np.ndarray):
         return cls(cls._axes_from_bounds(bounds, axes, mappers))
 
     @staticmethod
-    def _axes_from_bounds(bounds, axes, mappers):
+    def _axes_from_bounds(bounds, axes, mappers, device=False):
         """1-D axis arrays from ``(lower, upper, npts)`` triples, one per dimension.
 
         ``axes``/``mappers``: indices of the axes to map and the mapper for each, called as
@@ -282,8 +339,18 @@ class Grid(np.ndarray):
                 )
             mapper_of = dict(zip(idx.tolist(), mappers))
 
+        # A mapped axis is built as the reference builds it (grid.py:203): the call
+        # ``mapper(*((bound[2],) + bound[:2]))`` — which is also what makes a *list* bound of a
+        # mapped axis a TypeError there (tuple + list), kept here.
+        if device:       # DeviceGrid: nodes generated on the GPU, bit-identical to the host formulas
+            return tuple(
+                (cheb_device(*((bound[2],) + bound[:2])) if mapper_of[k] is cheb
+                 else mapper_of[k](*((bound[2],) + bound[:2]))) if k in mapper_of
+                else _linspace_device(*bound)
+                for k, bound in enumerate(bounds)
+            )
         return tuple(
-            mapper_of[k](bound[2], bound[0], bound[1]) if k in mapper_of else np.linspace(*bound)
+            mapper_of[k](*((bound[2],) + bound[:2])) if k in mapper_of else np.linspace(*bound)
             for k, bound in enumerate(bounds)
         )
 
@@ -467,7 +534,7 @@ def drop_last_grid():
 
 
 def drop_all_grids():
-    """Empty the grid registry."""
-    nums = _get_grid_manager().nums()
-    if nums:
-        drop_grid(num=nums)
+    """Drop every registered grid.  Like the reference (grid.py:608-610) this is
+    ``drop_grid(num=manager.nums())``, so on an EMPTY registry it raises TypeError (an empty list is
+    not an array of integers) — callers that may find the registry empty check ``nums()`` first."""
+    drop_grid(num=_get_grid_manager().nums())

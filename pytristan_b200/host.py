@@ -6,11 +6,33 @@ whole fields — H2D on one copy stream, the operator kernels on the caller's st
 second copy stream, double buffered — so that the PCIe transfers of neighbouring chunks overlap
 each other and the kernels.  This is what bench.py's ``e2e`` figure measures.
 """
+import os
+
 import numpy as np
 
 from . import _lib
 
-__all__ = ["apply_host", "launches_per_apply"]
+__all__ = ["apply_host", "launches_per_apply", "bind_rank_to_cores"]
+
+
+def bind_rank_to_cores(local_rank, local_world):
+    """One process per GPU: give this rank its own contiguous share of the host cores this job may
+    run on (``sched_setaffinity``), so that the copy-issuing threads and the pinned buffers they
+    first touch of different ranks do not migrate over each other.  Call it before allocating
+    pinned memory.  Returns the list of cores now owned (all of them if there are fewer cores than
+    ranks or the platform has no affinity call)."""
+    if not hasattr(os, "sched_getaffinity"):
+        return []
+    cores = sorted(os.sched_getaffinity(0))
+    per = len(cores) // max(1, int(local_world))
+    if per < 1:
+        return cores
+    mine = cores[int(local_rank) * per:(int(local_rank) + 1) * per]
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return cores
+    return mine
 
 _streams = {}
 
@@ -37,7 +59,8 @@ def apply_host(ops, fields, outs=None, chunk_fields=None):
     ``fields``: ndarray or CPU torch tensor holding B flat fields (pinned memory makes the
     copies asynchronous).  ``outs``: optional list of host buffers of the same size, one per
     operator; allocated (pinned) when omitted.  Returns the list of outputs, same kind as
-    ``fields``.  All operators must be bound to the same grid.
+    ``fields``, after the last device-to-host copy has completed (the host buffers are safe to
+    read on return).  All operators must be bound to the same grid.
     """
     torch = _lib.require_cuda()
     ops = list(ops)
@@ -99,8 +122,11 @@ def apply_host(ops, fields, outs=None, chunk_fields=None):
             ev_out[slot].record(s_out)
     cur.wait_stream(s_out)
     cur.wait_stream(s_in)
+    # the outputs are HOST memory: they are valid only once the last device-to-host copy has
+    # landed, so the call returns after waiting for it on the host (ndarray or tensor alike); the
+    # asynchronous reads of `fields` have completed by then too (they precede the kernels)
+    ev_out[(nchunks - 1) % slots].synchronize()
     if as_numpy:
-        cur.synchronize()
         return [o.numpy().reshape(np.shape(fields)) for o in outs_t]
     return [o.view(u.shape) for o in outs_t]
 

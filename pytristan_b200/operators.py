@@ -158,6 +158,11 @@ class _DiffMat(np.ndarray):
     @classmethod
     def _wrap(cls, d_mat, npts, axis, order, grid_num):
         host = d_mat.cpu().numpy()
+        # The device-resident forms below are what apply()/@ read.  The host entries are therefore
+        # frozen: an in-place edit (D[0, :] = 0 ...) would silently leave the GPU applying the old
+        # operator.  Boundary rows go through solve.with_rows / solve.dirichlet; a writable
+        # ``D.copy()`` is a plain matrix whose device forms are rebuilt on every use (_cacheable).
+        host.setflags(write=False)
         obj = host.view(cls)
         obj.axis, obj.order, obj.npts, obj.grid_num = axis, order, tuple(npts), grid_num
         obj._key = None
@@ -165,6 +170,8 @@ class _DiffMat(np.ndarray):
         obj._packed = None
         obj._band = None
         obj._eo = None
+        if EVEN_ODD:
+            obj._eo_forms()          # eligibility + packed halves now, not inside the first apply()
         return obj
 
     @property
@@ -172,42 +179,57 @@ class _DiffMat(np.ndarray):
         """Registry key ``[grid, axis, order(, accuracy)]`` or None when unregistered."""
         return self._key
 
+    @property
+    def _cacheable(self):
+        """Device forms are cached only while the host entries cannot change (read-only array)."""
+        return not self.flags.writeable
+
     def device(self):
-        """Row-major ``n x n`` CUDA tensor holding the same entries as the ndarray."""
-        if self._dev is None:
-            self._dev = _lib.to_device(np.asarray(self), dtype=np.float64)
-        return self._dev
+        """Row-major ``n_out x n_in`` CUDA tensor holding the same entries as the ndarray."""
+        if self._dev is not None and self._cacheable:
+            return self._dev
+        dev = _lib.to_device(np.ascontiguousarray(self), dtype=np.float64)
+        self._dev = dev if self._cacheable else None
+        return dev
 
     def _packed_device(self):
-        if self._packed is None:
-            lib = _lib.load()
-            d = self.device()
-            n_out, n_in = int(self.shape[0]), int(self.shape[1])
-            packed = _lib.empty((lib.pt_packed_size(n_out, n_in),))
-            _lib.check(
-                lib.pt_operator_pack(_lib.dptr(d), n_out, n_in, n_in, _lib.dptr(packed),
-                                     _lib.stream_ptr()),
-                "pt_operator_pack",
-            )
-            self._packed = packed
-        return self._packed
+        if self._packed is not None and self._cacheable:
+            return self._packed
+        lib = _lib.load()
+        d = self.device()
+        n_out, n_in = int(self.shape[0]), int(self.shape[1])
+        packed = _lib.empty((lib.pt_packed_size(n_out, n_in),))
+        _lib.check(
+            lib.pt_operator_pack(_lib.dptr(d), n_out, n_in, n_in, _lib.dptr(packed),
+                                 _lib.stream_ptr()),
+            "pt_operator_pack",
+        )
+        self._packed = packed if self._cacheable else None
+        return packed
 
     def _eo_forms(self):
         """``(sign, packed_even, packed_odd)`` when the operator is centro(anti)symmetric to within
-        EO_TOLERANCE (decided once, on the device), else None."""
+        EO_TOLERANCE, else None.  Decided on the device when the operator is built (``_wrap``), so
+        that ``apply`` never allocates or synchronises; the verdict of ``pt_operator_symmetry`` lands
+        in a caller-owned device scalar and is read back here, on the Python side."""
+        if not self._cacheable:
+            return None               # writable copy: entries may change, plain kernel every time
         if getattr(self, "_eo", None) is None:
             self._eo = False
             n = int(self.shape[0])
             if self.ndim == 2 and self.shape[0] == self.shape[1] and n >= 16:
                 lib = _lib.load()
+                torch = _lib.torch_mod()
                 d = self.device()
                 order = getattr(self, "order", None)
                 signs = (1, -1) if order is None else ((1,) if order % 2 == 0 else (-1,))
-                for sign in signs:
-                    worst = ctypes.c_double(0.0)
-                    _lib.check(lib.pt_operator_symmetry(_lib.dptr(d), n, sign, ctypes.byref(worst),
+                d_worst = torch.zeros(len(signs), dtype=torch.float64, device="cuda")
+                for k, sign in enumerate(signs):
+                    _lib.check(lib.pt_operator_symmetry(_lib.dptr(d), n, sign, _lib.dptr(d_worst[k:]),
                                                         _lib.stream_ptr()), "pt_operator_symmetry")
-                    if worst.value <= EO_TOLERANCE:
+                worst = d_worst.cpu().tolist()
+                for sign, w in zip(signs, worst):
+                    if w <= EO_TOLERANCE:
                         size = lib.pt_packed_eo_size(n)
                         pe, po = _lib.empty((size,)), _lib.empty((size,))
                         _lib.check(lib.pt_operator_pack_eo(_lib.dptr(d), n, _lib.dptr(pe), _lib.dptr(po),
@@ -316,31 +338,46 @@ class _DiffMat(np.ndarray):
         )
 
     def matmul(self, other):
-        """``D @ other``: ``other`` with leading dimension ``n`` is multiplied as a matrix
-        (``D @ M``); a flat field (or stack of fields) on the bound grid is differentiated along
-        the bound axis (the Kronecker-lifted product ``L_k @ u`` without forming ``L_k``)."""
+        """``D @ other``.
+
+        Whole fields on the bound grid are differentiated along the bound axis (the
+        Kronecker-lifted product ``L_k @ u`` without forming ``L_k``): an operand whose last
+        extent is ``prod(npts)``, or a flat vector holding a whole number of fields.  Anything else
+        with leading extent ``n_in`` is multiplied as a matrix (``D @ M``), also for row/column
+        slices of an operator (``D[1:-1, :] @ u``: a non-square ``n_out x n_in`` product).  On a 1-D
+        grid (``prod(npts) == n``) a 2-D operand keeps NumPy's meaning, ``D @ M``; ``apply()`` is the
+        unambiguous entry point for stacks of fields."""
         torch = _lib.torch_mod()
-        shape = tuple(other.shape) if hasattr(other, "shape") else np.shape(other)
-        n = int(self.shape[1])
-        if len(shape) >= 1 and shape[0] == n and (self.npts is None or _prod(self.npts) != n
-                                                 or len(shape) > 1):
+        if not (isinstance(other, (np.ndarray, torch.Tensor)) or hasattr(other, "__dlpack__")):
+            other = np.asarray(other, dtype=np.float64)
+        shape = tuple(other.shape)
+        n_out, n_in = int(self.shape[0]), int(self.shape[1])
+        if self.npts is not None and self.axis is not None and len(shape) >= 1:
+            total = _prod(self.npts)
+            size = _prod(shape)
+            whole = total > 0 and size % total == 0
+            if whole and (len(shape) == 1 or (shape[-1] == total and total != n_in)):
+                return self.apply(other)
+        if len(shape) >= 1 and shape[0] == n_in:
             d_u, kind = _field_to_device(other)
-            cols = d_u.numel() // n
+            cols = d_u.numel() // n_in
             d_y = self._matrix_product(d_u, cols)
+            out_shape = (n_out,) + shape[1:]
             if kind == "numpy":
-                return d_y.cpu().numpy().reshape(shape)
-            return d_y.view(shape)
-        if isinstance(other, (np.ndarray, torch.Tensor)) or hasattr(other, "__dlpack__"):
-            return self.apply(other)
-        return self.apply(np.asarray(other, dtype=np.float64))
+                return d_y.cpu().numpy().reshape(out_shape)
+            return d_y.view(out_shape)
+        if self.npts is None:
+            raise ValueError(f"matmul: operand of shape {shape} does not match the {n_out} x {n_in} matrix "
+                             "(views of an operator are plain matrices, not bound to a grid)")
+        return self.apply(other)
 
     def _matrix_product(self, d_u, cols):
+        """``D @ M`` for the ``n_out x n_in`` matrix of this array (plain DMMA kernel)."""
         lib = _lib.load()
-        torch = _lib.torch_mod()
-        n = int(self.shape[1])
-        d_y = torch.empty_like(d_u)
+        n_out, n_in = int(self.shape[0]), int(self.shape[1])
+        d_y = _lib.empty((n_out * cols,))
         _lib.check(
-            lib.pt_dense_apply(_lib.dptr(self._packed_device()), n, n, _lib.dptr(d_u),
+            lib.pt_dense_apply(_lib.dptr(self._packed_device()), n_out, n_in, _lib.dptr(d_u),
                                _lib.dptr(d_y), 1, cols, 1.0, 0.0, None, _lib.SCALE_NONE, 0,
                                _lib.stream_ptr()),
             "pt_dense_apply",
@@ -352,7 +389,7 @@ class _DiffMat(np.ndarray):
 
     def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
         if ufunc is np.matmul and method == "__call__" and out is None and inputs[0] is self \
-                and self.npts is not None:
+                and self.ndim == 2:
             return self.matmul(inputs[1])
         args = [np.asarray(i) if isinstance(i, _DiffMat) else i for i in inputs]
         if out is not None:
@@ -596,6 +633,8 @@ class FinDiffMat(_DiffMat):
         return d_y
 
     def _matrix_product(self, d_u, cols):
+        if self._band is None or self.shape[0] != self.shape[1]:
+            return super()._matrix_product(d_u, cols)     # row/column slice: a plain dense matrix
         return self._apply_device(d_u, 1, int(self.shape[1]), cols, None, 1.0, 0.0, None, None)
 
 

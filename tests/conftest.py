@@ -55,12 +55,21 @@ def cpu_expand(monkeypatch):
     yield
 
 
+def clear_grids():
+    """Empty the grid registry.  ``drop_all_grids()`` on an empty registry raises TypeError, as in
+    the reference (grid.py:608-610), so look before dropping."""
+    import pytristan_b200 as pt
+
+    if pt._get_grid_manager().nums():
+        pt.drop_all_grids()
+
+
 @pytest.fixture
 def clean_registries():
     import pytristan_b200 as pt
 
-    pt.drop_all_grids()
+    clear_grids()
     pt.drop_all_mats()
     yield
-    pt.drop_all_grids()
+    clear_grids()
     pt.drop_all_mats()

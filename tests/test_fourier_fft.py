@@ -2,6 +2,7 @@
 against the dense tensor-core path: same linear map, componentwise within 1e-12 of |D||u|."""
 import numpy as np
 import pytest
+from conftest import clear_grids
 
 from oracle import operators as oracle
 
@@ -100,7 +101,7 @@ def test_polar_laplacian_with_fft_azimuthal_operator():
     the FFT and the 1/r^2 scaling fused in its store phase (PT_SCALE_AFTER)."""
     import pytristan_b200 as pt
 
-    pt.drop_all_grids()
+    clear_grids()
     g = pt.get_polar_grid(64, 24, axes=[1], mappers=[pt.cheb], fornberg=True)
     lap = pt.PolarLaplacian(g, azimuthal="fft")
     dense = pt.PolarLaplacian(g)
@@ -113,7 +114,7 @@ def test_polar_laplacian_with_fft_azimuthal_operator():
     assert np.linalg.norm(y - dense.apply(U)) / np.linalg.norm(yref) <= 1e-12
     assert np.max(np.abs(lap.apply(R ** 3 * np.cos(3 * T)))) < 1e-8
     assert np.max(np.abs(lap.apply(R ** 2) - 4.0)) < 1e-8
-    pt.drop_all_grids()
+    clear_grids()
 
 
 def test_fft_after_scale_strided_axis():

@@ -138,6 +138,35 @@ def test_device_grid_matches_host_grid():
         g.axpoints(3)
 
 
+@pytest.mark.parametrize("case", ["channel", "polar_fornberg", "cheb3d"])
+def test_device_grid_nodes_are_generated_on_the_device_bit_for_bit(case):
+    """DeviceGrid.from_bounds builds its 1-D nodes on the GPU (pt_gen_linspace, pt_gen_cheb_libm)
+    and reads them back through pt_grid_axpoints: same bits as the host Grid (= the reference's)."""
+    import pytristan_b200 as pt
+
+    if case == "channel":
+        bounds, axes = [(0.0, 2 * np.pi - 2 * np.pi / 1024, 1024), (-1.0, 1.0, 257)], [1]
+    elif case == "polar_fornberg":
+        bounds, axes = [(-np.pi, np.pi - 2.0 * np.pi / 1024, 1024), (-1.0, 1.0, 1024)], [1]
+    else:
+        bounds, axes = [(-1.0, 1.0, 96), (0.0, 3.0, 65), (-2.0, 5.0, 33)], [0, 1, 2]
+    mappers = [pt.cheb] * len(axes)
+    host = pt.Grid.from_bounds(*bounds, axes=axes, mappers=mappers)
+    dev = pt.DeviceGrid.from_bounds(*bounds, axes=axes, mappers=mappers)
+    assert dev.npts == host.npts
+    assert dev.tensor.cpu().numpy().tobytes() == np.asarray(host).tobytes()
+    for k in range(len(bounds)):
+        assert dev.axpoints(k).tobytes() == host.axpoints(k).tobytes()
+        assert dev.axpoints_device(k).is_cuda
+    # a user mapper that is not `cheb` is called on the host, as the reference does
+    stretch = lambda n, lo, hi: lo + (hi - lo) * np.linspace(0.0, 1.0, n) ** 2   # noqa: E731
+    h2 = pt.Grid.from_bounds((0.0, 1.0, 17), (0.0, 2.0, 9), axes=[1], mappers=[stretch])
+    d2 = pt.DeviceGrid.from_bounds((0.0, 1.0, 17), (0.0, 2.0, 9), axes=[1], mappers=[stretch])
+    assert d2.tensor.cpu().numpy().tobytes() == np.asarray(h2).tobytes()
+    with pytest.raises(TypeError):
+        pt.DeviceGrid.from_bounds([0.0, 1.0, 5], axes=[0], mappers=[pt.cheb])      # list bound of a mapped axis
+
+
 def test_device_grid_config4_size():
     """The 1024^3 mesh of BASELINE config 4 (24 GiB, not materialisable by the reference on this
     host) built on the device; checked through slices and checksums."""

@@ -4,6 +4,7 @@ grid construction bit-exact; derivatives within 1e-12 componentwise relative to 
 1e-12 normwise on the N(0,1) synthetic fields."""
 import numpy as np
 import pytest
+from conftest import clear_grids
 
 from oracle import operators as oracle
 
@@ -328,7 +329,7 @@ def test_stencil_polynomial_exactness():
 def test_polar_laplacian():
     import pytristan_b200 as pt
 
-    pt.drop_all_grids()
+    clear_grids()
     g = pt.get_polar_grid(64, 24, axes=[1], mappers=[pt.cheb], fornberg=True)
     lap = pt.PolarLaplacian(g)
     th, r = g.axpoints(0), g.axpoints(1)
@@ -342,7 +343,7 @@ def test_polar_laplacian():
     f = R ** 3 * np.cos(3 * T)
     assert np.max(np.abs(lap.apply(f))) < 1e-8
     assert np.max(np.abs(lap.apply(R ** 2) - 4.0)) < 1e-8
-    pt.drop_all_grids()
+    clear_grids()
 
 
 @pytest.mark.parametrize("dims", [(5, 7, 9), (33, 65, 34), (1, 40, 70)])

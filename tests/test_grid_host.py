@@ -66,6 +66,17 @@ def test_from_bounds_error_types():
         Grid.from_bounds((0.0, 1.0, 3), (0.0, 1.0, 3), axes=[1, -1], mappers=[cheb, cheb])
 
 
+def test_mapped_axis_bound_must_be_a_tuple_like_the_reference(cpu_expand):
+    """Reference grid.py:203 builds the mapper call as ``(bound[2],) + bound[:2]``: a list bound of a
+    MAPPED axis is a TypeError there (tuple + list); unmapped axes accept lists (np.linspace(*bound))."""
+    Grid.from_bounds([0.0, 1.0, 3])                                   # unmapped: fine
+    Grid.from_bounds((0.0, 1.0, 3), axes=[0], mappers=[cheb])        # mapped tuple: fine
+    with pytest.raises(TypeError):
+        Grid.from_bounds([0.0, 1.0, 3], axes=[0], mappers=[cheb])
+    with pytest.raises(TypeError):
+        Grid.from_bounds(np.array([0.0, 1.0, 3.0]), axes=[0], mappers=[cheb])   # npts arrives as a float
+
+
 def test_from_arrs_rejects():
     with pytest.raises(ValueError):
         Grid.from_arrs(np.arange(4).reshape(2, 2))
@@ -207,7 +218,8 @@ def test_drop_sequences():
     assert mgr.nums() == [0, 1, 3, 4]
     drop_all_grids()
     assert mgr.nums() == []
-    drop_all_grids()          # empty registry: nothing to do, no error
+    with pytest.raises(TypeError):
+        drop_all_grids()      # empty registry: drop_grid(num=[]) -> TypeError, as in the reference (grid.py:608-610)
 
 
 def test_object_manager_composite_keys():
