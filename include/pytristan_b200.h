@@ -157,6 +157,21 @@ int pt_dense_apply_eo(const double* packed_even, const double* packed_odd, int n
                       double beta, const double* scale, int scale_mode, int64_t scale_len,
                       pt_stream_t stream);
 
+/* The same operation by the warp-specialised kernel (csrc/dense_apply_eo_ws.cu): producer warps stage
+ * the operator panels with the bulk-copy engine (cp.async.bulk, one 32 KB request per k chunk) and
+ * form E / O once per 128 half-rows, consumer warps run LDS + DMMA only, mbarrier ring, no CTA
+ * barrier.  Bit-identical to pt_dense_apply_eo for even n; for odd n the middle row / column are
+ * rank-1 terms beside an exactly (n-1)/2-sized half problem.  The operator is packed once per
+ * (128-row block, k chunk): pt_packed_eo_ws_size(n) doubles filled by pt_operator_pack_eo_ws.
+ * Returns PT_ERR_UNSUPPORTED — nothing done, no message — for shapes it does not cover (n < 128,
+ * fewer tiles than SMs, odd strides or odd n on the contiguous axis, unaligned fields): callers
+ * then use pt_dense_apply_eo. */
+int64_t pt_packed_eo_ws_size(int n);
+int pt_operator_pack_eo_ws(const double* D, int n, double* packed_ws, pt_stream_t stream);
+int pt_dense_apply_eo_ws(const double* packed_ws, int n, int sign, const double* U, double* Y,
+                         int64_t after, int64_t before, double alpha, double beta, const double* scale,
+                         int scale_mode, int64_t scale_len, pt_stream_t stream);
+
 /* ---- FourMat through the FFT ----------------------------------------- */
 /* tw[2*m], tw[2*m+1] = cos, -sin of 2 pi m / n for m < n (n complex doubles); n a power of two. */
 int pt_fourier_twiddles(int n, double* tw, pt_stream_t stream);
@@ -268,6 +283,10 @@ int pt_dense_apply_scatter(const double* packed, int n_out, int n_in, const doub
 int pt_dense_apply_eo_scatter(const double* packed_even, const double* packed_odd, int n, int sign,
                               const double* U, const double* C, int64_t after, int64_t before,
                               double alpha, double beta, const pt_scatter_map* map, pt_stream_t stream);
+/* ... and by the warp-specialised kernel (pt_dense_apply_eo_ws; PT_ERR_UNSUPPORTED likewise). */
+int pt_dense_apply_eo_ws_scatter(const double* packed_ws, int n, int sign, const double* U, const double* C,
+                                 int64_t after, int64_t before, double alpha, double beta,
+                                 const pt_scatter_map* map, pt_stream_t stream);
 /* The same redistribution for an array that is only moved (the field itself): 16-byte peer
  * stores, no staging buffer, no pack/unpack pass.  before == 1 requires s_i == 1. */
 int pt_peer_scatter(const double* src, int n, int64_t after, int64_t before,

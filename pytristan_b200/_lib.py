@@ -87,6 +87,12 @@ SIGNATURES = {
                                    _c_ptr, _c_i32, _c_i64, _c_ptr]),
     "pt_dense_apply_eo_scatter": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64,
                                            _c_f64, ctypes.POINTER(ScatterMap), _c_ptr]),
+    "pt_packed_eo_ws_size": (_c_i64, [_c_i32]),
+    "pt_operator_pack_eo_ws": (_c_i32, [_c_ptr, _c_i32, _c_ptr, _c_ptr]),
+    "pt_dense_apply_eo_ws": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64, _c_f64,
+                                      _c_ptr, _c_i32, _c_i64, _c_ptr]),
+    "pt_dense_apply_eo_ws_scatter": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64,
+                                              _c_f64, ctypes.POINTER(ScatterMap), _c_ptr]),
     "pt_fourier_twiddles": (_c_i32, [_c_i32, _c_ptr, _c_ptr]),
     "pt_fourier_apply": (_c_i32, [_c_ptr, _c_i32, _c_f64, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64, _c_f64,
                                   _c_ptr, _c_i64, _c_ptr]),

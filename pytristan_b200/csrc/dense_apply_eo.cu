@@ -13,31 +13,12 @@
 // the same thread, and the epilogue writes rows i and n-1-i — no extra pass over the field, no
 // extra HBM traffic.  Layout conventions, staging (cp.async ring, fragment-major operator panels,
 // pitch = 4 mod 16) and the fused alpha/beta/scale/scatter epilogue are those of dense_apply.cu.
-#include "dense_common.cuh"
+#include "dense_eo_common.cuh"
 #include <string.h>
 
 using namespace ptdense;
 
 namespace {
-
-struct EoParams {
-  const double* __restrict__ Dpe;   // packed Ae: [KPH/2][MPH][8] (k-panel PAIRS, 8 consecutive k per row)
-  const double* __restrict__ Dpo;   // packed Ao
-  const double* __restrict__ U;
-  double* __restrict__ Y;
-  const double* __restrict__ C;     // beta input (== Y unless scattering)
-  const double* __restrict__ scale;
-  ScatterDev sc;
-  int n, H;                         // operator size, half size ceil(n/2)
-  int MPH, KPH;                     // padded half rows, k-panels of the half problem (KPH is even)
-  int rt_per_block, m_blocks;       // row-tiles (8 half-rows) per tile, tiles along the half-rows
-  int64_t total_tiles;              // m_blocks * column tiles
-  int sign;                         // +1: J D J = D, -1: J D J = -D
-  int64_t before, NN, slab;         // slab = n*before
-  double alpha, beta;
-  int scale_mode;
-  int64_t scale_len;
-};
 
 // WARPS_M x WARPS_N warps; a warp owns up to WR row-tiles of the half problem (each with an even and
 // an odd accumulator set) x WN column tiles.
@@ -48,11 +29,14 @@ struct EoCfg {
   static constexpr int BN = WARPS_N * WN * 8;
   static constexpr int BK = BKP * 4;
   static constexpr int A_STAGE = BKP * 2 * BMH * 4;                 // per panel PAIR: [even rows][odd rows] x 8
-  // field tile pitch.  K1 ([k][column], 8-byte fragment reads of rows 2t and 2t+1): BN + 2 puts the
-  // 16 lanes of a half-warp in 16 different banks.  K2 ([column][k], 16-byte fragment reads): no
-  // padding; for 16-wide k chunks the 16-byte pieces of odd columns are stored XOR 4 (swizzle), so
-  // that the 8 lanes of a quarter-warp (2 columns x 4 pieces) cover all 8 bank groups.
-  static constexpr int PB = KCONTIG ? BK : (BN + 2);
+  // field tile pitch: no padding, XOR swizzles instead (a padded pitch that is not a multiple of
+  // 128 bytes costs the 16-byte cp.async writes 2-3 shared-memory wavefronts each: ncu r02a).
+  // K1 ([k][column], 8-byte fragment reads of rows 2t and 2t+1): column index XOR 4*((k >> 1) & 3)
+  // puts the 16 lanes of a half-warp (4 k rows x 4 columns) in 16 different bank pairs.  K2
+  // ([column][k], 16-byte fragment reads): for 16-wide k chunks the 16-byte pieces of odd columns
+  // are stored XOR 4, so that the 8 lanes of a quarter-warp (2 columns x 4 pieces) cover all 8 bank
+  // groups.
+  static constexpr int PB = KCONTIG ? BK : BN;
   static constexpr int SWZ = (KCONTIG && BK == 16) ? 4 : 0;     // piece-index XOR of odd columns
   static constexpr int B_TILE = KCONTIG ? BN * PB : BK * PB;
   static constexpr int STAGE = A_STAGE + 2 * B_TILE;                // field tile + mirrored field tile
@@ -65,7 +49,8 @@ struct EoCfg {
 // groups of 4 is a valid pair of DMMA k-panels); the field fragments follow the same assignment.
 template <class C, int RT, int WR, int WN, bool KCONTIG, bool VEC16>
 __device__ __forceinline__ void eo_frags(const double* As, const double* B1, const double* B2, int pr, int swz,
-                                         double2 (&ae)[WR], double2 (&ao)[WR], double2 (&be)[WN], double2 (&bo)[WN]) {
+                                         const int (&bcol)[WN], double2 (&ae)[WR], double2 (&ao)[WR],
+                                         double2 (&be)[WN], double2 (&bo)[WN]) {
 #pragma unroll
   for (int i = 0; i < RT; ++i) {
     ae[i] = *reinterpret_cast<const double2*>(As + (pr * 2 * C::BMH + i * 8) * 8);
@@ -82,8 +67,9 @@ __device__ __forceinline__ void eo_frags(const double* As, const double* B1, con
       // mirrored tile: 16-byte copies keep the memory order inside a pair, i.e. the pair is swapped
       if (VEC16) { f2a = v2.y; f2b = v2.x; } else { f2a = v2.x; f2b = v2.y; }
     } else {
-      f1a = B1[pr * 8 * C::PB + j * 8]; f1b = B1[(pr * 8 + 1) * C::PB + j * 8];
-      f2a = B2[pr * 8 * C::PB + j * 8]; f2b = B2[(pr * 8 + 1) * C::PB + j * 8];
+      // B1/B2 point at row 2t of the tile; bcol[j] is the swizzled column of this lane
+      f1a = B1[pr * 8 * C::PB + bcol[j]]; f1b = B1[(pr * 8 + 1) * C::PB + bcol[j]];
+      f2a = B2[pr * 8 * C::PB + bcol[j]]; f2b = B2[(pr * 8 + 1) * C::PB + bcol[j]];
     }
     be[j] = make_double2(__dadd_rn(f1a, f2a), __dadd_rn(f1b, f2b));
     bo[j] = make_double2(__dsub_rn(f1a, f2a), __dsub_rn(f1b, f2b));
@@ -92,13 +78,13 @@ __device__ __forceinline__ void eo_frags(const double* As, const double* B1, con
 
 template <class C, int RT, int WR, int WN, int BKP, bool KCONTIG, bool VEC16>
 __device__ __forceinline__ void eo_compute(const double* As, const double* B1, const double* B2, int npairs, int swz,
-                                           double (&acce)[WR][WN][2], double (&acco)[WR][WN][2]) {
+                                           const int (&bcol)[WN], double (&acce)[WR][WN][2], double (&acco)[WR][WN][2]) {
   static_assert(BKP % 2 == 0, "k-panels are processed in pairs");
   if (npairs == BKP / 2) {
 #pragma unroll
     for (int pr = 0; pr < BKP / 2; ++pr) {
       double2 ae[WR], ao[WR], be[WN], bo[WN];
-      eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pr, swz, ae, ao, be, bo);
+      eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pr, swz, bcol, ae, ao, be, bo);
       // consecutive DMMAs share their A operand (operand reuse), as in the plain kernel
 #pragma unroll
       for (int i = 0; i < RT; ++i) {
@@ -119,7 +105,7 @@ __device__ __forceinline__ void eo_compute(const double* As, const double* B1, c
 #pragma unroll 1
     for (int pr = 0; pr < npairs; ++pr) {
       double2 ae[WR], ao[WR], be[WN], bo[WN];
-      eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pr, swz, ae, ao, be, bo);
+      eo_frags<C, RT, WR, WN, KCONTIG, VEC16>(As, B1, B2, pr, swz, bcol, ae, ao, be, bo);
 #pragma unroll
       for (int i = 0; i < RT; ++i)
 #pragma unroll
@@ -137,15 +123,16 @@ __device__ __forceinline__ void eo_compute(const double* As, const double* B1, c
 template <class C, int RT, int WR, int WN, int BKP, bool KCONTIG, bool VEC16>
 struct EoDispatch {
   static __device__ __forceinline__ void run(int my_rt, const double* As, const double* B1, const double* B2,
-                                             int npairs, int swz, double (&acce)[WR][WN][2], double (&acco)[WR][WN][2]) {
-    if (my_rt == RT) eo_compute<C, RT, WR, WN, BKP, KCONTIG, VEC16>(As, B1, B2, npairs, swz, acce, acco);
-    else EoDispatch<C, RT - 1, WR, WN, BKP, KCONTIG, VEC16>::run(my_rt, As, B1, B2, npairs, swz, acce, acco);
+                                             int npairs, int swz, const int (&bcol)[WN], double (&acce)[WR][WN][2],
+                                             double (&acco)[WR][WN][2]) {
+    if (my_rt == RT) eo_compute<C, RT, WR, WN, BKP, KCONTIG, VEC16>(As, B1, B2, npairs, swz, bcol, acce, acco);
+    else EoDispatch<C, RT - 1, WR, WN, BKP, KCONTIG, VEC16>::run(my_rt, As, B1, B2, npairs, swz, bcol, acce, acco);
   }
 };
 template <class C, int WR, int WN, int BKP, bool KCONTIG, bool VEC16>
 struct EoDispatch<C, 0, WR, WN, BKP, KCONTIG, VEC16> {
   static __device__ __forceinline__ void run(int, const double*, const double*, const double*, int, int,
-                                             double (&)[WR][WN][2], double (&)[WR][WN][2]) {}
+                                             const int (&)[WN], double (&)[WR][WN][2], double (&)[WR][WN][2]) {}
 };
 
 template <int WARPS_M, int WARPS_N, int WR, int WN, int BKP, int STAGES, bool KCONTIG, bool VEC16, int MINB, bool SCAT>
@@ -254,8 +241,9 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
         const bool ok = b_col_ok && (k < n);
         const double* s1 = ok ? b_base + int64_t(k) * p.before : p.U;
         const double* s2 = ok ? b_base + int64_t(n - 1 - k) * p.before : p.U;
-        double* d1 = B1 + kr * C::PB + b_cc * EPC;
-        double* d2 = B2 + kr * C::PB + b_cc * EPC;
+        const int cs = (b_cc * EPC) ^ (4 * ((kr >> 1) & 3));      // K1 swizzle (EoCfg)
+        double* d1 = B1 + kr * C::PB + cs;
+        double* d2 = B2 + kr * C::PB + cs;
         if (VEC16) { cp_async16(d1, s1, ok ? 16 : 0); cp_async16(d2, s2, ok ? 16 : 0); }
         else { cp_async8(d1, s1, ok ? 8 : 0); cp_async8(d2, s2, ok ? 8 : 0); }
       }
@@ -309,6 +297,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
     for (int r = 0; r < BR; ++r) {
       const bool ok = (b_ok >> (KCONTIG ? r : 0)) & 1u;
       int so = (b_r0 + r * RPP) * C::PB + b_cc * EPC;
+      if (!KCONTIG) so = (b_r0 + r * RPP) * C::PB + ((b_cc * EPC) ^ (4 * (((b_r0 + r * RPP) >> 1) & 3)));
       if (KCONTIG && C::SWZ) {          // column parity is constant over r (RPP is even)
         const int sw = (b_r0 & 1) ? C::SWZ : 0;
         so = (b_r0 + r * RPP) * C::PB + (VEC16 ? ((b_cc ^ sw) * 2) : ((((b_cc >> 1) ^ sw) << 1) | (b_cc & 1)));
@@ -343,13 +332,14 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
   // B fragment: k = t, column = g.  In the mirrored tile of the contiguous-axis kernel a 16-byte
   // piece holds (u[n-2-k], u[n-1-k]): the slot of mirrored index k is k ^ 1.
   // (the pair swap of the mirrored tile is undone when the fragments are read, eo_frags)
-  const int b1_off = KCONTIG ? ((wn * WN * 8 + g) * C::PB + 2 * t) : (2 * t * C::PB + wn * WN * 8 + g);
+  const int b1_off = KCONTIG ? ((wn * WN * 8 + g) * C::PB + 2 * t) : (2 * t * C::PB);
   const int b2_off = b1_off;
+  int bcol[WN];                                       // K1: swizzled column of this lane in column tile j
+#pragma unroll
+  for (int j = 0; j < WN; ++j) bcol[j] = (wn * WN * 8 + j * 8 + g) ^ (4 * t);
   const int frag_swz = (C::SWZ && (g & 1)) ? 1 : 0;   // odd columns of a swizzled tile: pair index XOR 1
   const int nfull = p.KPH / BKP;
   const int tail = (p.KPH - nfull * BKP) / 2;        // panel pairs of the last, partial chunk
-  const bool use_beta = (p.beta != 0.0);
-  const double sgn = double(p.sign);
 
   for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const int m_block = int(tile % p.m_blocks);
@@ -379,77 +369,11 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) dense_apply_eo_ke
       const double* B2 = B1 + C::B_TILE;
       ++consumed;
       EoDispatch<C, WR, WR, WN, BKP, KCONTIG, VEC16>::run(my_rt, As + a_off, B1 + b1_off, B2 + b2_off,
-                                                          kc < nfull ? BKP / 2 : tail, frag_swz, acce, acco);
+                                                          kc < nfull ? BKP / 2 : tail, frag_swz, bcol, acce, acco);
     }
 
     // ---- epilogue: rows i (ze + zo) and n-1-i (s*(ze - zo)) --------------------------------------------
-#pragma unroll
-    for (int j = 0; j < WN; ++j) {
-      const int64_t nn = n0 + (wn * WN + j) * 8 + 2 * t;
-      if (nn >= p.NN) continue;
-      const bool two = (nn + 1 < p.NN);
-      int64_t a0, b0, a1, b1;
-      if (KCONTIG) {
-        a0 = nn; b0 = 0; a1 = nn + 1; b1 = 0;
-      } else {
-        a0 = nn / p.before; b0 = nn - a0 * p.before;
-        if (b0 + 1 < p.before) { a1 = a0; b1 = b0 + 1; } else { a1 = a0 + 1; b1 = 0; }
-      }
-      double s0 = p.alpha, s1 = p.alpha;
-      if (p.scale_mode == PT_SCALE_AFTER) {
-        s0 *= p.scale[a0 % p.scale_len];
-        if (two) s1 *= p.scale[a1 % p.scale_len];
-      } else if (p.scale_mode == PT_SCALE_BEFORE) {
-        s0 *= p.scale[b0];
-        if (two) s1 *= p.scale[b1];
-      }
-      const int64_t l0 = a0 * p.slab + b0, l1 = a1 * p.slab + b1;
-      int64_t d0 = 0, d1 = 0;
-      if (SCAT) {
-        const int64_t q0 = a0 / p.sc.a_inner, q1 = a1 / p.sc.a_inner;
-        d0 = p.sc.offset + q0 * p.sc.s_outer + (a0 - q0 * p.sc.a_inner) * p.sc.s_inner + b0;
-        d1 = p.sc.offset + q1 * p.sc.s_outer + (a1 - q1 * p.sc.a_inner) * p.sc.s_inner + b1;
-      }
-#pragma unroll
-      for (int i = 0; i < WR; ++i) {
-        if (i >= my_rt) continue;
-        const int hrow = m0h + (my_rt0 + i) * 8 + g;
-        if (hrow >= p.H) continue;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int row = half == 0 ? hrow : n - 1 - hrow;
-          if (half == 1 && row == hrow) continue;          // middle row of an odd n: written once
-          double w0, w1;
-          if (half == 0) { w0 = __dadd_rn(acce[i][j][0], acco[i][j][0]); w1 = __dadd_rn(acce[i][j][1], acco[i][j][1]); }
-          else { w0 = __dmul_rn(sgn, __dsub_rn(acce[i][j][0], acco[i][j][0])); w1 = __dmul_rn(sgn, __dsub_rn(acce[i][j][1], acco[i][j][1])); }
-          double r0 = s0, r1 = s1;
-          if (p.scale_mode == PT_SCALE_ROW) { const double sr = p.scale[row]; r0 *= sr; r1 *= sr; }
-          double v0 = __dmul_rn(r0, w0), v1 = __dmul_rn(r1, w1);
-          const int64_t off = int64_t(row) * p.before;
-          const double* c0 = (SCAT ? p.C : p.Y) + l0 + off;
-          const double* c1 = (SCAT ? p.C : p.Y) + l1 + off;
-          double *y0, *y1;
-          if (SCAT) {
-            const int dq = row / p.sc.chunk;
-            double* db = p.sc.base[dq] + int64_t(row - dq * p.sc.chunk) * p.sc.s_i;
-            y0 = db + d0; y1 = db + d1;
-          } else {
-            y0 = p.Y + l0 + off; y1 = p.Y + l1 + off;
-          }
-          if (!KCONTIG && VEC16) {
-            if (use_beta) { const double2 o = *reinterpret_cast<const double2*>(c0); v0 = __fma_rn(p.beta, o.x, v0); v1 = __fma_rn(p.beta, o.y, v1); }
-            *reinterpret_cast<double2*>(y0) = make_double2(v0, v1);
-          } else {
-            if (use_beta) v0 = __fma_rn(p.beta, *c0, v0);
-            *y0 = v0;
-            if (two) {
-              if (use_beta) v1 = __fma_rn(p.beta, *c1, v1);
-              *y1 = v1;
-            }
-          }
-        }
-      }
-    }
+    eo_epilogue<WR, WN, KCONTIG, VEC16, SCAT, false>(p, acce, acco, my_rt, m0h + my_rt0 * 8, n0 + wn * WN * 8, g, t);
   }
   cp_async_wait<0>();
 }
@@ -562,6 +486,7 @@ int apply_eo_impl(const double* pe, const double* po, int n, int sign, const dou
   p.before = before; p.NN = after * before; p.slab = int64_t(n) * before;
   p.alpha = alpha; p.beta = beta; p.scale_mode = scale_mode; p.scale_len = scale_len > 0 ? scale_len : 1;
   p.m_blocks = 1; p.rt_per_block = 1; p.total_tiles = 0;
+  p.cmid = nullptr; p.rmid = nullptr; p.dmm = 0.0; p.mid = -1;
   cudaStream_t st = pt::as_stream(stream);
   if (before == 1) {
     const bool vec = (n % 2 == 0) && aligned16(U);

@@ -1,0 +1,554 @@
+// K1/K2 for centrosymmetric operators, warp-specialised form (the default for large fields).
+//
+// Same algebra and the same per-accumulator summation order as dense_apply_eo.cu (results are
+// bit-identical for even n); what changes is who does what inside the CTA:
+//
+//   * 8 CONSUMER warps (2 x 4, each 64 half-rows x 16 columns, an even and an odd accumulator set)
+//     do nothing but LDS + DMMA: they wait on a "full" mbarrier per ring stage, read the operator
+//     fragments and the E / O fragments, and release the stage through an "empty" mbarrier.  No
+//     __syncthreads, no loads, no address arithmetic, no DADD in their instruction stream.
+//   * 4 PRODUCER warps (one warpgroup, shrunk to 120 registers with setmaxnreg so that the consumers
+//     can keep 192) own the data movement: one elected lane asks the bulk-copy engine for the
+//     operator panels of the chunk (ONE cp.async.bulk of 32 KB: the operator is packed per
+//     (128-row block, k chunk) for exactly this), all lanes load the field tile and its mirror image
+//     from global memory, form E = u + Ju and O = u - Ju once per 128 half-rows (the cp.async kernel
+//     forms them per warp and per 64 half-rows, on the FP64 pipe the DMMAs need) and store them into
+//     the stage (swizzled, conflict-free for both sides).
+//   * odd n (config 2's n = 257): the half problem is (n-1)/2 x (n-1)/2 exactly (H = 128, no 17th
+//     row tile, no 33rd k panel); the middle COLUMN is a rank-1 term added to the even accumulator in
+//     the epilogue (one FMA per element), the middle ROW is a dot product the producers accumulate
+//     from the E (or O) values they form anyway.
+//
+// One CTA per SM (192 KB ring of 4 stages), persistent over tiles (m fastest).
+#include "dense_eo_common.cuh"
+
+using namespace ptdense;
+
+namespace {
+
+constexpr int CW_M = 2, CW_N = 4, WR = 8, WN = 2;       // consumer warps and their tiles
+constexpr int NCONS = CW_M * CW_N * 32;                 // 256 consumer threads
+constexpr int NPROD = 128;                              // 4 producer warps = one warpgroup
+constexpr int NPASS = 4;                                // passes of the producers over a chunk
+constexpr int NT = NCONS + NPROD;
+constexpr int BMH = CW_M * WR * 8;                      // 128 half-rows per tile
+constexpr int BN = CW_N * WN * 8;                       // 64 columns per tile
+constexpr int BK = 16;                                  // k per chunk = 2 panel pairs
+constexpr int STAGES = 4;
+constexpr int A_PAIR = 2 * BMH * 8;                     // doubles of one panel pair: [e|o][128][8]
+constexpr int A_STAGE = 2 * A_PAIR;                     // 4096 doubles = 32 KB
+constexpr int B_TILE = BN * BK;                         // 1024 doubles = 8 KB (E tile; O tile follows)
+constexpr int STAGE = A_STAGE + 2 * B_TILE;             // 48 KB
+constexpr size_t SMEM_RING = size_t(STAGES) * STAGE * sizeof(double);
+constexpr size_t SMEM_BYTES = SMEM_RING + 2 * STAGES * sizeof(uint64_t) + 2 * 3 * BN * sizeof(double);
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ double2 ldg2(const double* p) {
+  return __ldg(reinterpret_cast<const double2*>(p));
+}
+// barrier among the producer warps only (named barrier 1)
+__device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+
+// ---- consumer: DMMAs of one staged chunk, specialised on the exact number of row tiles ------------
+template <int RT, bool KCONTIG>
+__device__ __forceinline__ void ws_compute(const double* As, const double* Et, const double* Ot, int npairs,
+                                           int swz, const int (&bcol)[WN], double (&acce)[WR][WN][2],
+                                           double (&acco)[WR][WN][2]) {
+#pragma unroll
+  for (int pr = 0; pr < 2; ++pr) {
+    if (pr < npairs) {
+      double2 ae[WR], ao[WR], be[WN], bo[WN];
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+        ae[i] = *reinterpret_cast<const double2*>(As + pr * A_PAIR + i * 64);
+        ao[i] = *reinterpret_cast<const double2*>(As + pr * A_PAIR + BMH * 8 + i * 64);
+      }
+#pragma unroll
+      for (int j = 0; j < WN; ++j) {
+        if (KCONTIG) {          // [column][16 k]: one 16-byte read gives k = 8P + 2t and 8P + 2t + 1
+          be[j] = *reinterpret_cast<const double2*>(Et + j * 8 * BK + (pr ^ swz) * 8);
+          bo[j] = *reinterpret_cast<const double2*>(Ot + j * 8 * BK + (pr ^ swz) * 8);
+        } else {                // [k][64 columns], column XOR 4*((k >> 1) & 3)
+          be[j] = make_double2(Et[pr * 8 * BN + bcol[j]], Et[(pr * 8 + 1) * BN + bcol[j]]);
+          bo[j] = make_double2(Ot[pr * 8 * BN + bcol[j]], Ot[(pr * 8 + 1) * BN + bcol[j]]);
+        }
+      }
+      // per accumulator: panel (k = 8P + 2t) before panel (k = 8P + 2t + 1), pairs in order — the
+      // summation order of dense_apply_eo.cu
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+#pragma unroll
+        for (int j = 0; j < WN; ++j) dmma(acce[i][j][0], acce[i][j][1], ae[i].x, be[j].x);
+#pragma unroll
+        for (int j = 0; j < WN; ++j) dmma(acco[i][j][0], acco[i][j][1], ao[i].x, bo[j].x);
+      }
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+#pragma unroll
+        for (int j = 0; j < WN; ++j) dmma(acce[i][j][0], acce[i][j][1], ae[i].y, be[j].y);
+#pragma unroll
+        for (int j = 0; j < WN; ++j) dmma(acco[i][j][0], acco[i][j][1], ao[i].y, bo[j].y);
+      }
+    }
+  }
+}
+
+template <int RT, bool KCONTIG>
+struct WsDispatch {
+  static __device__ __forceinline__ void run(int my_rt, const double* As, const double* Et, const double* Ot,
+                                             int npairs, int swz, const int (&bcol)[WN], double (&acce)[WR][WN][2],
+                                             double (&acco)[WR][WN][2]) {
+    if (my_rt == RT) ws_compute<RT, KCONTIG>(As, Et, Ot, npairs, swz, bcol, acce, acco);
+    else WsDispatch<RT - 1, KCONTIG>::run(my_rt, As, Et, Ot, npairs, swz, bcol, acce, acco);
+  }
+};
+template <bool KCONTIG>
+struct WsDispatch<0, KCONTIG> {
+  static __device__ __forceinline__ void run(int, const double*, const double*, const double*, int, int,
+                                             const int (&)[WN], double (&)[WR][WN][2], double (&)[WR][WN][2]) {}
+};
+
+template <bool KCONTIG, bool SCAT, bool MIDFIX>
+__global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams p) {
+  extern __shared__ __align__(128) double smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + SMEM_RING);
+  uint64_t* empty = full + STAGES;
+  double* midbuf = reinterpret_cast<double*>(empty + STAGES);       // [2 tile parities][3 warps][BN]
+
+  const int tid = threadIdx.x;
+  const int n = p.n, H = p.H;
+  const int npanel_pairs = (H + 7) >> 3;               // pairs of k-panels = groups of 8 k
+  const int nchunks = (npanel_pairs + 1) >> 1;
+  const int tail_pairs = npanel_pairs & 1;             // 1: the last chunk holds one pair only
+  const int rtiles_total = (H + 7) >> 3;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, NPROD + 1); mbar_init(empty + s, CW_M * CW_N); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= NCONS) {
+    // =============================== producers ====================================================
+    // Two chunks of global loads are kept in flight (two register sets): the loads of chunk i + 1 are
+    // issued before the E/O stores of chunk i wait for their ring slot, so the DRAM latency of a
+    // chunk never adds to the time the producers need per chunk.  A LOAD iterator and a STORE
+    // iterator walk the same (tile, chunk) sequence one chunk apart.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;\n");
+    const int ptid = tid - NCONS;
+    // tile-independent part of this thread's addressing
+    const int c2 = KCONTIG ? 2 * (ptid & 7) : 0;              // K2: first k of the 16-byte piece
+    const int colp = ptid >> 3;                               // K2: column of pass 0
+    const int kr0 = KCONTIG ? 0 : (ptid >> 5);                // K1: k row of pass 0
+    const int sto = KCONTIG ? colp * BK + (((ptid & 7) ^ ((colp & 1) ? 4 : 0)) << 1)   // odd columns: piece XOR 4
+                            : 2 * (ptid & 31);                // K1: column pair of the tile
+    const int64_t pass_step = KCONTIG ? int64_t(16) * n : 4 * p.before;
+    const int64_t chunk_step = KCONTIG ? int64_t(BK) : int64_t(BK) * p.before;
+    const int64_t my_tiles = (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t total_it = my_tiles * nchunks;
+
+    // ---- load iterator -------------------------------------------------------------------------------
+    int64_t l_tile = blockIdx.x;
+    int l_kc = 0;
+    const double *l_fwd = p.U, *l_mir = p.U;
+    unsigned l_ok = 0;
+    auto l_setup = [&](int64_t tile) {
+      const int64_t n0 = (tile / p.m_blocks) * BN;
+      l_ok = 0;
+      if (KCONTIG) {
+        l_fwd = p.U + (n0 + colp) * n + c2;
+        l_mir = p.U + (n0 + colp) * n + (n - 2 - c2);
+#pragma unroll
+        for (int r = 0; r < NPASS; ++r)
+          if (n0 + colp + 16 * r < p.NN) l_ok |= 1u << r;
+      } else {
+        const int64_t nn = n0 + sto;
+        int64_t la = 0;
+        if (nn < p.NN) {
+          l_ok = 0xfu;
+          const int64_t a = nn / p.before;
+          la = a * p.slab + (nn - a * p.before);
+        }
+        l_fwd = p.U + la + int64_t(kr0) * p.before;
+        l_mir = p.U + la + int64_t(n - 1 - kr0) * p.before;
+      }
+    };
+    auto load = [&](double2 (&f)[NPASS], double2 (&m)[NPASS]) {
+      const int k0 = l_kc * BK;
+#pragma unroll
+      for (int r = 0; r < NPASS; ++r) {
+        // K2: pieces k0 + c2, k0 + c2 + 1 of column colp + 16r; K1: row k0 + kr0 + 4r of the column pair
+        const bool ok = KCONTIG ? (((l_ok >> r) & 1u) && (k0 + c2 < H)) : (l_ok && (k0 + kr0 + 4 * r < H));
+        if (ok) {
+          f[r] = ldg2(l_fwd + r * pass_step);
+          m[r] = ldg2(KCONTIG ? l_mir + r * pass_step : l_mir - r * pass_step);
+        } else {
+          f[r] = make_double2(0.0, 0.0);
+          m[r] = make_double2(0.0, 0.0);
+        }
+      }
+      l_fwd += chunk_step;
+      l_mir -= chunk_step;
+      if (++l_kc == nchunks) {
+        l_kc = 0;
+        l_tile += gridDim.x;
+        if (l_tile < p.total_tiles) l_setup(l_tile);
+      }
+    };
+
+    // ---- store iterator ------------------------------------------------------------------------------
+    int64_t s_tile = blockIdx.x;
+    int s_kc = 0, s_mblock = int(s_tile % p.m_blocks);
+    unsigned it = 0;
+    double macc0 = 0.0, macc1 = 0.0;   // MIDFIX: this thread's part of the middle row's dot product
+    auto store = [&](const double2 (&f)[NPASS], const double2 (&m)[NPASS]) {
+      const int slot = it % STAGES;
+      const unsigned round = it / STAGES;
+      if (round > 0) mbar_wait(empty + slot, (round - 1) & 1u);
+      double* As = smem + size_t(slot) * STAGE;
+      double* Et = As + A_STAGE;
+      double* Ot = Et + B_TILE;
+      if (ptid == 0) {
+        const int npairs = (s_kc == nchunks - 1 && tail_pairs) ? 1 : 2;
+        const unsigned bytes = unsigned(npairs) * A_PAIR * sizeof(double);
+        mbar_arrive_expect_tx(full + slot, bytes);
+        bulk_g2s(As, p.Dpe + (size_t(s_mblock) * nchunks + s_kc) * A_STAGE, bytes, full + slot);
+      }
+      const int k0 = s_kc * BK;
+#pragma unroll
+      for (int r = 0; r < NPASS; ++r) {
+        double2 e, o;
+        if (KCONTIG) {      // the mirrored piece holds (u[n-2-k], u[n-1-k]): pair swapped
+          e = make_double2(__dadd_rn(f[r].x, m[r].y), __dadd_rn(f[r].y, m[r].x));
+          o = make_double2(__dsub_rn(f[r].x, m[r].y), __dsub_rn(f[r].y, m[r].x));
+          *reinterpret_cast<double2*>(Et + sto + r * (16 * BK)) = e;       // 16 columns further: same parity
+          *reinterpret_cast<double2*>(Ot + sto + r * (16 * BK)) = o;
+        } else {
+          e = make_double2(__dadd_rn(f[r].x, m[r].x), __dadd_rn(f[r].y, m[r].y));
+          o = make_double2(__dsub_rn(f[r].x, m[r].x), __dsub_rn(f[r].y, m[r].y));
+          const int kr = kr0 + 4 * r;
+          const int so = kr * BN + (sto ^ (4 * ((kr >> 1) & 3)));
+          *reinterpret_cast<double2*>(Et + so) = e;
+          *reinterpret_cast<double2*>(Ot + so) = o;
+          if (MIDFIX && s_mblock == 0 && k0 + kr < H) {
+            const double rk = p.rmid[k0 + kr];
+            const double2 x = p.sign > 0 ? e : o;
+            macc0 = __fma_rn(rk, x.x, macc0);
+            macc1 = __fma_rn(rk, x.y, macc1);
+          }
+        }
+      }
+      mbar_arrive(full + slot);
+      ++it;
+      if (++s_kc < nchunks) return;
+      // ---- end of a tile ---------------------------------------------------------------------------
+      if (MIDFIX && !KCONTIG) {
+        // middle row of an odd n: y[mid] = sum_k D[mid][k] X[k] + D[mid][mid] u[mid]; producer warp w
+        // holds the k rows = w (mod 4) of every column pair
+        double* buf = midbuf + ((s_tile / gridDim.x) & 1) * (3 * BN);
+        if (s_mblock == 0 && kr0 > 0) { buf[(kr0 - 1) * BN + sto] = macc0; buf[(kr0 - 1) * BN + sto + 1] = macc1; }
+        producer_sync();
+        const int64_t nn = (s_tile / p.m_blocks) * BN + sto;
+        if (s_mblock == 0 && kr0 == 0 && nn < p.NN) {
+          const double w0 = __dadd_rn(__dadd_rn(__dadd_rn(macc0, buf[sto]), buf[BN + sto]), buf[2 * BN + sto]);
+          const double w1 = __dadd_rn(__dadd_rn(__dadd_rn(macc1, buf[sto + 1]), buf[BN + sto + 1]), buf[2 * BN + sto + 1]);
+          const int64_t a = nn / p.before, b = nn - a * p.before;
+          const int64_t off = a * p.slab + b + int64_t(p.mid) * p.before;
+          const double2 um = ldg2(p.U + off);
+          const double dmm = p.rmid[nchunks * BK];
+          const double t0 = __fma_rn(dmm, um.x, w0), t1 = __fma_rn(dmm, um.y, w1);
+          double s0 = p.alpha, s1 = p.alpha;
+          if (p.scale_mode == PT_SCALE_AFTER) { s0 *= p.scale[a % p.scale_len]; s1 = s0; }
+          else if (p.scale_mode == PT_SCALE_BEFORE) { s0 *= p.scale[b]; s1 *= p.scale[b + 1]; }
+          else if (p.scale_mode == PT_SCALE_ROW) { const double sr = p.scale[p.mid]; s0 *= sr; s1 *= sr; }
+          double v0 = __dmul_rn(s0, t0), v1 = __dmul_rn(s1, t1);
+          if (p.beta != 0.0) {
+            const double2 o = *reinterpret_cast<const double2*>((SCAT ? p.C : p.Y) + off);
+            v0 = __fma_rn(p.beta, o.x, v0);
+            v1 = __fma_rn(p.beta, o.y, v1);
+          }
+          double* y;
+          if (SCAT) {
+            const int dq = p.mid / p.sc.chunk;
+            const int64_t q = a / p.sc.a_inner;
+            y = p.sc.base[dq] + int64_t(p.mid - dq * p.sc.chunk) * p.sc.s_i + p.sc.offset + q * p.sc.s_outer +
+                (a - q * p.sc.a_inner) * p.sc.s_inner + b;
+          } else {
+            y = p.Y + off;
+          }
+          *reinterpret_cast<double2*>(y) = make_double2(v0, v1);
+        }
+        macc0 = 0.0;
+        macc1 = 0.0;
+      }
+      s_kc = 0;
+      s_tile += gridDim.x;
+      s_mblock = int(s_tile % p.m_blocks);
+    };
+
+    double2 f0[NPASS], m0[NPASS], f1[NPASS], m1[NPASS];
+    l_setup(l_tile);
+    load(f0, m0);
+    for (int64_t i = 0; i < total_it; i += 2) {
+      if (i + 1 < total_it) load(f1, m1);
+      store(f0, m0);
+      if (i + 2 < total_it) load(f0, m0);
+      if (i + 1 < total_it) store(f1, m1);
+    }
+    return;
+  }
+
+  // ================================= consumers ======================================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 192;\n");
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wn = warp % CW_N, wm = warp / CW_N;
+  const int g = lane >> 2, t = lane & 3;
+  int bcol[WN];
+#pragma unroll
+  for (int j = 0; j < WN; ++j) bcol[j] = (wn * WN * 8 + j * 8 + g) ^ (4 * t);
+  const int b_off = KCONTIG ? ((wn * WN * 8 + g) * BK + 2 * t) : (2 * t * BN);
+  const int frag_swz = KCONTIG ? (g & 1) : 0;
+  unsigned it = 0;
+  for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int m_block = int(tile % p.m_blocks);
+    const int64_t n0 = (tile / p.m_blocks) * BN;
+    const int rt0 = m_block * (BMH / 8);
+    const int rt_count = min(BMH / 8, rtiles_total - rt0);
+    const int q = (rt_count + CW_M - 1) / CW_M;
+    const int my_rt0 = wm * q;
+    const int my_rt = max(0, min(q, rt_count - my_rt0));
+    const int a_off = my_rt0 * 64 + 2 * lane;
+
+    double acce[WR][WN][2], acco[WR][WN][2];
+#pragma unroll
+    for (int i = 0; i < WR; ++i)
+#pragma unroll
+      for (int j = 0; j < WN; ++j) { acce[i][j][0] = acce[i][j][1] = 0.0; acco[i][j][0] = acco[i][j][1] = 0.0; }
+
+    for (int kc = 0; kc < nchunks; ++kc, ++it) {
+      const int slot = it % STAGES;
+      mbar_wait(full + slot, (it / STAGES) & 1u);
+      const double* As = smem + size_t(slot) * STAGE;
+      const double* Et = As + A_STAGE + b_off;
+      const double* Ot = Et + B_TILE;
+      const int npairs = (kc == nchunks - 1 && tail_pairs) ? 1 : 2;
+      WsDispatch<WR, KCONTIG>::run(my_rt, As + a_off, Et, Ot, npairs, frag_swz, bcol, acce, acco);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + slot);
+    }
+    eo_epilogue<WR, WN, KCONTIG, true, SCAT, MIDFIX>(p, acce, acco, my_rt, rt0 * 8 + my_rt0 * 8, n0 + wn * WN * 8, g, t);
+  }
+}
+
+// operator halves in the layout the bulk copy wants: [m_block][chunk][pair][e|o][128 rows][8 k]
+__global__ void pack_eo_ws_kernel(const double* __restrict__ D, int n, int H, int m_blocks, int nchunks,
+                                  double* __restrict__ out) {
+  const int64_t total = int64_t(m_blocks) * nchunks * A_STAGE;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int kk = int(idx & 7);
+    const int row = int((idx >> 3) & (BMH - 1));
+    const int eo = int((idx >> 10) & 1);
+    const int pair = int((idx >> 11) & 1);
+    const int64_t blk = idx >> 12;
+    const int kc = int(blk % nchunks), mb = int(blk / nchunks);
+    const int i = mb * BMH + row, k = (kc * 2 + pair) * 8 + kk;
+    double v = 0.0;
+    if (i < H && k < H) {
+      const double a = D[int64_t(i) * n + k], b = D[int64_t(i) * n + (n - 1 - k)];
+      v = eo == 0 ? __dmul_rn(0.5, __dadd_rn(a, b)) : __dmul_rn(0.5, __dsub_rn(a, b));
+    }
+    out[idx] = v;
+  }
+  // odd n: middle column, middle row, middle element after the panels
+  if (n & 1) {
+    const int mid = (n - 1) / 2;
+    double* cmid = out + total;
+    double* rmid = cmid + int64_t(m_blocks) * BMH;
+    for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < int64_t(m_blocks) * BMH;
+         idx += int64_t(gridDim.x) * blockDim.x)
+      cmid[idx] = idx < H ? D[idx * n + mid] : 0.0;
+    for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx <= int64_t(nchunks) * BK;
+         idx += int64_t(gridDim.x) * blockDim.x)
+      rmid[idx] = idx < H ? D[int64_t(mid) * n + idx] : (idx == int64_t(nchunks) * BK ? D[int64_t(mid) * n + mid] : 0.0);
+  }
+}
+
+inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
+
+int g_ws_enabled = 1;      // tuning hook: pt_debug_set_eo_config(60 / 61) = never / default
+
+struct WsShape {
+  int H, m_blocks, nchunks;
+  int64_t panels;          // doubles of the packed panels
+};
+WsShape ws_shape(int n) {
+  WsShape s;
+  s.H = n / 2;
+  s.m_blocks = (s.H + BMH - 1) / BMH;
+  const int pairs = (s.H + 7) / 8;
+  s.nchunks = (pairs + 1) / 2;
+  s.panels = int64_t(s.m_blocks) * s.nchunks * A_STAGE;
+  return s;
+}
+
+template <bool KCONTIG, bool SCAT, bool MIDFIX>
+int launch_ws(EoParams& p, cudaStream_t stream) {
+  auto kern = dense_apply_eo_ws_kernel<KCONTIG, SCAT, MIDFIX>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  PT_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
+    attr_set[dev] = true;
+  }
+  int64_t grid = pt::sm_count();
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  kern<<<unsigned(grid), NT, SMEM_BYTES, stream>>>(p);
+  return pt::check_launch("pt_dense_apply_eo_ws");
+}
+
+}  // namespace
+
+namespace ptdense {
+
+int launch_eo_ws(EoParams& p, bool kcontig, bool scatter, cudaStream_t stream) {
+  const bool mid = p.mid >= 0;
+  if (kcontig) {
+    if (mid) return PT_ERR_UNSUPPORTED;
+    return scatter ? launch_ws<true, true, false>(p, stream) : launch_ws<true, false, false>(p, stream);
+  }
+  if (mid) return scatter ? launch_ws<false, true, true>(p, stream) : launch_ws<false, false, true>(p, stream);
+  return scatter ? launch_ws<false, true, false>(p, stream) : launch_ws<false, false, false>(p, stream);
+}
+
+}  // namespace ptdense
+
+namespace {
+
+// shapes the warp-specialised kernel covers; everything else runs dense_apply_eo.cu
+bool ws_eligible(int n, const double* U, const double* Y, const double* C, int64_t after, int64_t before,
+                 const pt_scatter_map* map) {
+  if (!g_ws_enabled || n < 128) return false;
+  const WsShape s = ws_shape(n);
+  const int64_t NN = after * before;
+  const int64_t tiles = int64_t(s.m_blocks) * ((NN + BN - 1) / BN);
+  if (tiles < pt::sm_count()) return false;            // small fields: the small-tile cp.async kernel fills the GPU better
+  if (!aligned16(U)) return false;
+  if (before == 1) return (n % 2) == 0;
+  if (before % 2) return false;
+  if (map) {
+    if ((map->s_outer | map->s_inner | map->s_i | map->offset) & 1) return false;
+    return C == nullptr || aligned16(C);
+  }
+  return aligned16(Y);
+}
+
+int apply_ws_impl(const double* packed, int n, int sign, const double* U, double* Y, const double* C, int64_t after,
+                  int64_t before, double alpha, double beta, const double* scale, int scale_mode, int64_t scale_len,
+                  const pt_scatter_map* map, pt_stream_t stream) {
+  PT_REQUIRE(packed && U, "pt_dense_apply_eo_ws: null pointer");
+  PT_REQUIRE(n >= 2, "pt_dense_apply_eo_ws: n=%d", n);
+  PT_REQUIRE(sign == 1 || sign == -1, "pt_dense_apply_eo_ws: sign must be +1 or -1");
+  PT_REQUIRE(after >= 0 && before >= 1, "pt_dense_apply_eo_ws: bad field shape");
+  PT_REQUIRE(scale_mode >= PT_SCALE_NONE && scale_mode <= PT_SCALE_BEFORE, "pt_dense_apply_eo_ws: bad scale_mode %d", scale_mode);
+  PT_REQUIRE(scale_mode == PT_SCALE_NONE || scale != nullptr, "pt_dense_apply_eo_ws: scale is null");
+  PT_REQUIRE(scale_mode != PT_SCALE_AFTER || scale_len > 0, "pt_dense_apply_eo_ws: scale_len must be > 0");
+  if (!ws_eligible(n, U, Y, C, after, before, map)) return PT_ERR_UNSUPPORTED;
+  if (after == 0) return PT_OK;
+  const WsShape s = ws_shape(n);
+  EoParams p;
+  p.Dpe = packed; p.Dpo = nullptr; p.U = U; p.Y = Y; p.C = C; p.scale = scale;
+  p.sc = map ? ScatterDev{map->base, map->chunk, map->a_inner, map->s_outer, map->s_inner, map->s_i, map->offset}
+             : ScatterDev{nullptr, 1, 1, 0, 0, 0, 0};
+  p.n = n; p.H = s.H; p.MPH = s.m_blocks * BMH; p.KPH = s.nchunks * 4;
+  p.rt_per_block = BMH / 8; p.m_blocks = s.m_blocks;
+  p.sign = sign;
+  p.before = before; p.NN = after * before; p.slab = int64_t(n) * before;
+  p.total_tiles = int64_t(s.m_blocks) * ((p.NN + BN - 1) / BN);
+  p.alpha = alpha; p.beta = beta; p.scale_mode = scale_mode; p.scale_len = scale_len > 0 ? scale_len : 1;
+  p.cmid = nullptr; p.rmid = nullptr; p.dmm = 0.0; p.mid = -1;
+  if (n & 1) {
+    p.mid = (n - 1) / 2;
+    p.cmid = packed + s.panels;
+    p.rmid = p.cmid + int64_t(s.m_blocks) * BMH;
+  }
+  return launch_eo_ws(p, before == 1, map != nullptr, pt::as_stream(stream));
+}
+
+}  // namespace
+
+extern "C" int pt_debug_set_eo_ws(int enabled) {
+  g_ws_enabled = enabled ? 1 : 0;
+  return PT_OK;
+}
+
+extern "C" int64_t pt_packed_eo_ws_size(int n) {
+  if (n < 2) return 0;
+  const WsShape s = ws_shape(n);
+  return s.panels + int64_t(s.m_blocks) * BMH + int64_t(s.nchunks) * BK + 1;
+}
+
+extern "C" int pt_operator_pack_eo_ws(const double* D, int n, double* packed, pt_stream_t stream) {
+  PT_REQUIRE(D && packed, "pt_operator_pack_eo_ws: null pointer");
+  PT_REQUIRE(n >= 2, "pt_operator_pack_eo_ws: n=%d", n);
+  const WsShape s = ws_shape(n);
+  int64_t blocks = (s.panels + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  pack_eo_ws_kernel<<<unsigned(blocks), 256, 0, pt::as_stream(stream)>>>(D, n, s.H, s.m_blocks, s.nchunks, packed);
+  return pt::check_launch("pt_operator_pack_eo_ws");
+}
+
+extern "C" int pt_dense_apply_eo_ws(const double* packed_ws, int n, int sign, const double* U, double* Y,
+                                    int64_t after, int64_t before, double alpha, double beta, const double* scale,
+                                    int scale_mode, int64_t scale_len, pt_stream_t stream) {
+  PT_REQUIRE(Y != nullptr, "pt_dense_apply_eo_ws: null pointer");
+  PT_REQUIRE(U != Y, "pt_dense_apply_eo_ws: in-place application is not supported");
+  return apply_ws_impl(packed_ws, n, sign, U, Y, Y, after, before, alpha, beta, scale, scale_mode, scale_len, nullptr,
+                       stream);
+}
+
+extern "C" int pt_dense_apply_eo_ws_scatter(const double* packed_ws, int n, int sign, const double* U, const double* C,
+                                            int64_t after, int64_t before, double alpha, double beta,
+                                            const pt_scatter_map* map, pt_stream_t stream) {
+  PT_REQUIRE(map && map->base, "pt_dense_apply_eo_ws_scatter: null map");
+  PT_REQUIRE(map->nranks >= 1 && map->chunk >= 1 && int64_t(map->chunk) * map->nranks >= n,
+             "pt_dense_apply_eo_ws_scatter: %d destinations x %d rows do not cover n=%d", map->nranks, map->chunk, n);
+  PT_REQUIRE(map->a_inner >= 1, "pt_dense_apply_eo_ws_scatter: a_inner must be >= 1");
+  PT_REQUIRE(beta == 0.0 || C != nullptr, "pt_dense_apply_eo_ws_scatter: beta != 0 needs C");
+  return apply_ws_impl(packed_ws, n, sign, U, nullptr, C ? C : U, after, before, alpha, beta, nullptr, PT_SCALE_NONE, 0,
+                       map, stream);
+}

@@ -131,6 +131,7 @@ def _field_to_device(u):
 # entries satisfy J D J = +-D to within EO_TOLERANCE (entrywise, relative) are applied as two
 # half-size tensor-core products.  Set EVEN_ODD = False to force the plain kernel.
 EVEN_ODD = True
+EVEN_ODD_WS = True          # large fields: the warp-specialised even-odd kernel (csrc/dense_apply_eo_ws.cu)
 EO_TOLERANCE = 4.0e-15
 
 
@@ -208,7 +209,7 @@ class _DiffMat(np.ndarray):
         return packed
 
     def _eo_forms(self):
-        """``(sign, packed_even, packed_odd)`` when the operator is centro(anti)symmetric to within
+        """``(sign, packed_even, packed_odd, packed_ws)`` when the operator is centro(anti)symmetric to within
         EO_TOLERANCE, else None.  Decided on the device when the operator is built (``_wrap``), so
         that ``apply`` never allocates or synchronises; the verdict of ``pt_operator_symmetry`` lands
         in a caller-owned device scalar and is read back here, on the Python side."""
@@ -234,7 +235,12 @@ class _DiffMat(np.ndarray):
                         pe, po = _lib.empty((size,)), _lib.empty((size,))
                         _lib.check(lib.pt_operator_pack_eo(_lib.dptr(d), n, _lib.dptr(pe), _lib.dptr(po),
                                                            _lib.stream_ptr()), "pt_operator_pack_eo")
-                        self._eo = (sign, pe, po)
+                        pw = None
+                        if n >= 128:      # large operators: also the layout of the warp-specialised kernel
+                            pw = _lib.empty((lib.pt_packed_eo_ws_size(n),))
+                            _lib.check(lib.pt_operator_pack_eo_ws(_lib.dptr(d), n, _lib.dptr(pw), _lib.stream_ptr()),
+                                       "pt_operator_pack_eo_ws")
+                        self._eo = (sign, pe, po, pw)
                         break
         return self._eo or None
 
@@ -302,6 +308,15 @@ class _DiffMat(np.ndarray):
                 raise ValueError("scale vector is too short")
         eo = self._eo_forms() if EVEN_ODD else None
         if eo is not None:
+            if eo[3] is not None and EVEN_ODD_WS:
+                # warp-specialised kernel (bulk-copied operator panels, mbarrier ring); -3 = shape not covered
+                rc = lib.pt_dense_apply_eo_ws(_lib.dptr(eo[3]), n, eo[0], _lib.dptr(d_u), _lib.dptr(d_y), after, before,
+                                              float(alpha), float(beta), _lib.dptr(d_scale), mode, slen,
+                                              _lib.stream_ptr())
+                if rc == 0:
+                    return d_y
+                if rc != -3:
+                    _lib.check(rc, "pt_dense_apply_eo_ws")
             _lib.check(
                 lib.pt_dense_apply_eo(_lib.dptr(eo[1]), _lib.dptr(eo[2]), n, eo[0], _lib.dptr(d_u), _lib.dptr(d_y),
                                       after, before, float(alpha), float(beta), _lib.dptr(d_scale), mode, slen,
@@ -323,6 +338,14 @@ class _DiffMat(np.ndarray):
         lib = _lib.load()
         eo = self._eo_forms() if EVEN_ODD else None
         if eo is not None:
+            if eo[3] is not None and EVEN_ODD_WS:
+                rc = lib.pt_dense_apply_eo_ws_scatter(_lib.dptr(eo[3]), n, eo[0], _lib.dptr(d_u), _lib.dptr(c), after,
+                                                      before, float(alpha), float(beta), ctypes.byref(smap),
+                                                      _lib.stream_ptr())
+                if rc == 0:
+                    return
+                if rc != -3:
+                    _lib.check(rc, "pt_dense_apply_eo_ws_scatter")
             _lib.check(
                 lib.pt_dense_apply_eo_scatter(_lib.dptr(eo[1]), _lib.dptr(eo[2]), n, eo[0], _lib.dptr(d_u),
                                               _lib.dptr(c), after, before, float(alpha), float(beta),

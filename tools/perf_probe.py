@@ -93,8 +93,45 @@ def real_op(kind, n, order, npts, axis, batch, label):
     ops_mod.EVEN_ODD = True
 
 
+def eo_variants(kind, n, order, npts, axis, batch, label):
+    """Centrosymmetric operators: warp-specialised kernel vs the cp.async even-odd kernel."""
+    import pytristan_b200.operators as ops_mod
+    x = np.arange(n) * (2 * np.pi / n) if kind == "four" else pt.cheb(n, -1.0, 1.0)
+    op = pt.FourMat(x, order=order) if kind == "four" else pt.ChebMat(x, order=order)
+    op.npts, op.axis = tuple(npts), axis
+    P = int(np.prod(npts))
+    nb = P * batch * 8
+    ring = [torch.randn(batch, P, dtype=torch.float64, device="cuda") for _ in range(max(1, min(4, int(6e8 // nb))))]
+    Y = torch.empty_like(ring[0])
+    fl = 2.0 * n * P * batch
+    for ws in (True, False):
+        ops_mod.EVEN_ODD_WS = ws
+        i = [0]
+
+        def run():
+            op.apply(ring[i[0] % len(ring)], out=Y)
+            i[0] += 1
+
+        ms = timeit(run, reps=8, warm=3)
+        print(json.dumps({"case": f"{label} [{'ws' if ws else 'cp.async'}]", "ms": round(ms, 4),
+                          "executed_tflops": round(fl / ms * 1e-9 / 2, 2),
+                          "executed_frac_peak": round(fl / ms * 1e-9 / 2 / PEAK_TF, 3), "gpts_s": round(P * batch / ms * 1e-6, 2)}))
+    ops_mod.EVEN_ODD_WS = True
+    del ring, Y
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "ws":
+        eo_variants("four", 1024, 1, (1024, 257), 0, 64, "cfg2 d/dx FourMat K2 n=1024")
+        eo_variants("cheb", 257, 2, (1024, 257), 1, 64, "cfg2 d2/dy2 ChebMat K1 n=257")
+        eo_variants("cheb", 512, 2, (1024, 512), 1, 64, "cfg3 radial K1 n=512 b64")
+        eo_variants("four", 1024, 2, (1024, 512), 0, 64, "cfg3 azimuthal K2 n=1024 b64")
+        eo_variants("cheb", 2048, 1, (8192, 2048), 1, 1, "cfg5a-1/8 ChebMat K1 n=2048")
+        eo_variants("cheb", 512, 2, (512, 512, 512), 0, 1, "cfg5b x K2 n=512")
+        eo_variants("cheb", 512, 2, (512, 512, 512), 1, 1, "cfg5b y K1 n=512")
+        eo_variants("cheb", 512, 2, (512, 512, 512), 2, 1, "cfg5b z K1 n=512")
+        sys.exit(0)
     if what == "eosmall":
         lib = _lib.load()
         for cfg in (1, 2, 0):
