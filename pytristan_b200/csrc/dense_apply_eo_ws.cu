@@ -7,8 +7,10 @@
 //     do nothing but LDS + DMMA: they wait on a "full" mbarrier per ring stage, read the operator
 //     fragments and the E / O fragments, and release the stage through an "empty" mbarrier.  No
 //     __syncthreads, no loads, no address arithmetic, no DADD in their instruction stream.
-//   * 4 PRODUCER warps (one warpgroup, shrunk to 120 registers with setmaxnreg so that the consumers
-//     can keep 192) own the data movement: one elected lane asks the bulk-copy engine for the
+//   * 8 PRODUCER warps (two warpgroups, shrunk to 64 registers with setmaxnreg so that the consumers
+//     can keep 192; two groups that alternate over the chunks, because a DADD issued behind two warps of
+//     back-to-back DMMAs waits ~150 cycles for the FP64 pipe — ncu r02c — and the wait is per warp)
+//     own the data movement: one elected lane asks the bulk-copy engine for the
 //     operator panels of the chunk (ONE cp.async.bulk of 32 KB: the operator is packed per
 //     (128-row block, k chunk) for exactly this), all lanes load the field tile and its mirror image
 //     from global memory, form E = u + Ju and O = u - Ju once per 128 half-rows (the cp.async kernel
@@ -17,7 +19,10 @@
 //   * odd n (config 2's n = 257): the half problem is (n-1)/2 x (n-1)/2 exactly (H = 128, no 17th
 //     row tile, no 33rd k panel); the middle COLUMN is a rank-1 term added to the even accumulator in
 //     the epilogue (one FMA per element), the middle ROW is a dot product the producers accumulate
-//     from the E (or O) values they form anyway.
+//     from the E (or O) values they form anyway (two independent DFMA chains per thread: a dependent
+//     chain waits for the FP64 pipe behind the DMMAs at every link); the eight partial sums of a column
+//     travel through shared memory with the tile's last chunk and the epilogue adds and stores them.
+//     (Accumulating in the consumer warps was measured: the DFMAs stall the DMMA stream, 0.24 vs 0.19 ms.)
 //
 // One CTA per SM (192 KB ring of 4 stages), persistent over tiles (m fastest).
 #include "dense_eo_common.cuh"
@@ -28,8 +33,9 @@ namespace {
 
 constexpr int CW_M = 2, CW_N = 4, WR = 8, WN = 2;       // consumer warps and their tiles
 constexpr int NCONS = CW_M * CW_N * 32;                 // 256 consumer threads
-constexpr int NPROD = 128;                              // 4 producer warps = one warpgroup
-constexpr int NPASS = 4;                                // passes of the producers over a chunk
+constexpr int NPROD = 256;                              // 8 producer warps: two groups of four, alternating chunks
+constexpr int PWARPS = NPROD / 32;
+constexpr int NPASS = 4;                                // passes of a producer group over a chunk
 constexpr int NT = NCONS + NPROD;
 constexpr int BMH = CW_M * WR * 8;                      // 128 half-rows per tile
 constexpr int BN = CW_N * WN * 8;                       // 64 columns per tile
@@ -40,7 +46,8 @@ constexpr int A_STAGE = 2 * A_PAIR;                     // 4096 doubles = 32 KB
 constexpr int B_TILE = BN * BK;                         // 1024 doubles = 8 KB (E tile; O tile follows)
 constexpr int STAGE = A_STAGE + 2 * B_TILE;             // 48 KB
 constexpr size_t SMEM_RING = size_t(STAGES) * STAGE * sizeof(double);
-constexpr size_t SMEM_BYTES = SMEM_RING + 2 * STAGES * sizeof(uint64_t) + 2 * 3 * BN * sizeof(double);
+constexpr size_t SMEM_FIXED = SMEM_RING + 2 * STAGES * sizeof(uint64_t) + (2 * BN + 2 * PWARPS * BN) * sizeof(double);
+constexpr size_t SMEM_MAX = 227 * 1024;                 // + cmid (odd n): MPH doubles
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
   return static_cast<unsigned>(__cvta_generic_to_shared(p));
@@ -78,8 +85,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 __device__ __forceinline__ double2 ldg2(const double* p) {
   return __ldg(reinterpret_cast<const double2*>(p));
 }
-// barrier among the producer warps only (named barrier 1)
-__device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
 
 // ---- consumer: DMMAs of one staged chunk, specialised on the exact number of row tiles ------------
 template <int RT, bool KCONTIG>
@@ -145,7 +150,10 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
   extern __shared__ __align__(128) double smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + SMEM_RING);
   uint64_t* empty = full + STAGES;
-  double* midbuf = reinterpret_cast<double*>(empty + STAGES);       // [2 tile parities][3 warps][BN]
+  double* umid_s = reinterpret_cast<double*>(empty + STAGES);       // [2 tile parities][BN]: u[mid] of the tile's columns
+  double* midbuf = umid_s + 2 * BN;                                 // [2 tile parities][8 producer warps][BN]: middle-row partial sums
+  double* cmid_s = midbuf + 2 * PWARPS * BN;                             // [MPH]: D[:, mid] (odd n only)
+  double* rmid_s = cmid_s + p.MPH;                                  // [nchunks * BK + 1]: D[mid, :], then D[mid][mid]
 
   const int tid = threadIdx.x;
   const int n = p.n, H = p.H;
@@ -155,19 +163,23 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
   const int rtiles_total = (H + 7) >> 3;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, NPROD + 1); mbar_init(empty + s, CW_M * CW_N); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, NPROD / 2 + 1); mbar_init(empty + s, CW_M * CW_N); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (MIDFIX) {
+    for (int i = tid; i < p.MPH; i += NT) cmid_s[i] = p.cmid[i];
+    for (int i = tid; i <= nchunks * BK; i += NT) rmid_s[i] = p.rmid[i];
   }
   __syncthreads();
 
   if (tid >= NCONS) {
     // =============================== producers ====================================================
-    // Two chunks of global loads are kept in flight (two register sets): the loads of chunk i + 1 are
-    // issued before the E/O stores of chunk i wait for their ring slot, so the DRAM latency of a
-    // chunk never adds to the time the producers need per chunk.  A LOAD iterator and a STORE
-    // iterator walk the same (tile, chunk) sequence one chunk apart.
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;\n");
-    const int ptid = tid - NCONS;
+    // Two groups of four warps; group g stages the chunks g, g + 2, g + 4, ... of this CTA's (tile, chunk)
+    // sequence.  A thread keeps ONE register set: right after it has stored chunk i it issues the global
+    // loads of chunk i + 2, which then have the other group's whole chunk to arrive.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
+    const int ptid = (tid - NCONS) & 127;
+    const int group = (tid - NCONS) >> 7;
     // tile-independent part of this thread's addressing
     const int c2 = KCONTIG ? 2 * (ptid & 7) : 0;              // K2: first k of the 16-byte piece
     const int colp = ptid >> 3;                               // K2: column of pass 0
@@ -179,153 +191,140 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
     const int64_t my_tiles = (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int64_t total_it = my_tiles * nchunks;
 
-    // ---- load iterator -------------------------------------------------------------------------------
-    int64_t l_tile = blockIdx.x;
-    int l_kc = 0;
-    const double *l_fwd = p.U, *l_mir = p.U;
-    unsigned l_ok = 0;
-    auto l_setup = [&](int64_t tile) {
+    // ---- position in the (tile, chunk) sequence + this thread's forward / mirrored source pointers ----
+    int64_t tile = blockIdx.x;
+    int kc = 0;
+    const double *fwd = p.U, *mir = p.U;
+    unsigned ok = 0;          // K2: validity of the column of each pass; K1: all-or-nothing
+    auto setup = [&]() {
       const int64_t n0 = (tile / p.m_blocks) * BN;
-      l_ok = 0;
+      ok = 0;
+      kc = 0;
       if (KCONTIG) {
-        l_fwd = p.U + (n0 + colp) * n + c2;
-        l_mir = p.U + (n0 + colp) * n + (n - 2 - c2);
+        fwd = p.U + (n0 + colp) * n + c2;
+        mir = p.U + (n0 + colp) * n + (n - 2 - c2);
 #pragma unroll
         for (int r = 0; r < NPASS; ++r)
-          if (n0 + colp + 16 * r < p.NN) l_ok |= 1u << r;
+          if (n0 + colp + 16 * r < p.NN) ok |= 1u << r;
       } else {
         const int64_t nn = n0 + sto;
         int64_t la = 0;
         if (nn < p.NN) {
-          l_ok = 0xfu;
+          ok = 0xfu;
           const int64_t a = nn / p.before;
           la = a * p.slab + (nn - a * p.before);
         }
-        l_fwd = p.U + la + int64_t(kr0) * p.before;
-        l_mir = p.U + la + int64_t(n - 1 - kr0) * p.before;
+        fwd = p.U + la + int64_t(kr0) * p.before;
+        mir = p.U + la + int64_t(n - 1 - kr0) * p.before;
       }
     };
-    auto load = [&](double2 (&f)[NPASS], double2 (&m)[NPASS]) {
-      const int k0 = l_kc * BK;
+    auto advance = [&]() {
+      fwd += chunk_step;
+      mir -= chunk_step;
+      if (++kc == nchunks) {
+        tile += gridDim.x;
+        if (tile < p.total_tiles) setup();
+        else ok = 0;
+      }
+    };
+
+    double2 f[NPASS], m[NPASS];
+    double2 um = make_double2(0.0, 0.0);     // MIDFIX: u[mid] of this thread's column pair (k row 0 warps)
+    auto load = [&]() {
+      const int k0 = kc * BK;
+      if (MIDFIX && kc == 0 && kr0 == 0 && ok) um = ldg2(fwd + int64_t(p.mid) * p.before);   // fwd is at row 0 here
 #pragma unroll
       for (int r = 0; r < NPASS; ++r) {
         // K2: pieces k0 + c2, k0 + c2 + 1 of column colp + 16r; K1: row k0 + kr0 + 4r of the column pair
-        const bool ok = KCONTIG ? (((l_ok >> r) & 1u) && (k0 + c2 < H)) : (l_ok && (k0 + kr0 + 4 * r < H));
-        if (ok) {
-          f[r] = ldg2(l_fwd + r * pass_step);
-          m[r] = ldg2(KCONTIG ? l_mir + r * pass_step : l_mir - r * pass_step);
+        const bool pok = KCONTIG ? (((ok >> r) & 1u) && (k0 + c2 < H)) : (ok && (k0 + kr0 + 4 * r < H));
+        if (pok) {
+          f[r] = ldg2(fwd + r * pass_step);
+          m[r] = ldg2(KCONTIG ? mir + r * pass_step : mir - r * pass_step);
         } else {
           f[r] = make_double2(0.0, 0.0);
           m[r] = make_double2(0.0, 0.0);
         }
       }
-      l_fwd += chunk_step;
-      l_mir -= chunk_step;
-      if (++l_kc == nchunks) {
-        l_kc = 0;
-        l_tile += gridDim.x;
-        if (l_tile < p.total_tiles) l_setup(l_tile);
-      }
     };
 
-    // ---- store iterator ------------------------------------------------------------------------------
-    int64_t s_tile = blockIdx.x;
-    int s_kc = 0, s_mblock = int(s_tile % p.m_blocks);
-    unsigned it = 0;
-    double macc0 = 0.0, macc1 = 0.0;   // MIDFIX: this thread's part of the middle row's dot product
-    auto store = [&](const double2 (&f)[NPASS], const double2 (&m)[NPASS]) {
+    double macc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};   // MIDFIX: middle-row partial sums, two independent chains
+    setup();
+    if (group == 1) advance();
+    unsigned it = group;
+    if (it < total_it) load();
+    while (it < total_it) {
+      // ---- chunk `it` = (tile, kc): registers -> E / O tiles of ring slot it % STAGES ----------------
       const int slot = it % STAGES;
       const unsigned round = it / STAGES;
-      if (round > 0) mbar_wait(empty + slot, (round - 1) & 1u);
+      const int mblock = int(tile % p.m_blocks);
+      const int par = int((tile / gridDim.x) & 1);
+      if (p.trace && ptid == 0) {
+        const long long t0 = clock64();
+        if (round > 0) mbar_wait(empty + slot, (round - 1) & 1u);
+        const int64_t ti = tile / gridDim.x;
+        if (ti < 16) {
+          long long* tr = p.trace + (int64_t(blockIdx.x) * 16 + ti) * 8;
+          tr[4] += clock64() - t0;                 // cycles the producers waited for a free slot
+          if (kc < 2) tr[5 + group] = t0;          // this group reaches the tile
+        }
+      } else if (round > 0) mbar_wait(empty + slot, (round - 1) & 1u);
       double* As = smem + size_t(slot) * STAGE;
       double* Et = As + A_STAGE;
       double* Ot = Et + B_TILE;
       if (ptid == 0) {
-        const int npairs = (s_kc == nchunks - 1 && tail_pairs) ? 1 : 2;
+        const int npairs = (kc == nchunks - 1 && tail_pairs) ? 1 : 2;
         const unsigned bytes = unsigned(npairs) * A_PAIR * sizeof(double);
         mbar_arrive_expect_tx(full + slot, bytes);
-        bulk_g2s(As, p.Dpe + (size_t(s_mblock) * nchunks + s_kc) * A_STAGE, bytes, full + slot);
+        bulk_g2s(As, p.Dpe + (size_t(mblock) * nchunks + kc) * A_STAGE, bytes, full + slot);
       }
-      const int k0 = s_kc * BK;
+      if (MIDFIX && kc == 0 && kr0 == 0)      // u[mid] of the tile's columns for the consumers' epilogue
+        *reinterpret_cast<double2*>(umid_s + par * BN + sto) = um;
+      // all FP64 work of the chunk in one burst (in place: E over f, O over m)
 #pragma unroll
       for (int r = 0; r < NPASS; ++r) {
-        double2 e, o;
+        const double2 a = f[r], b = m[r];
         if (KCONTIG) {      // the mirrored piece holds (u[n-2-k], u[n-1-k]): pair swapped
-          e = make_double2(__dadd_rn(f[r].x, m[r].y), __dadd_rn(f[r].y, m[r].x));
-          o = make_double2(__dsub_rn(f[r].x, m[r].y), __dsub_rn(f[r].y, m[r].x));
-          *reinterpret_cast<double2*>(Et + sto + r * (16 * BK)) = e;       // 16 columns further: same parity
-          *reinterpret_cast<double2*>(Ot + sto + r * (16 * BK)) = o;
+          f[r] = make_double2(__dadd_rn(a.x, b.y), __dadd_rn(a.y, b.x));
+          m[r] = make_double2(__dsub_rn(a.x, b.y), __dsub_rn(a.y, b.x));
         } else {
-          e = make_double2(__dadd_rn(f[r].x, m[r].x), __dadd_rn(f[r].y, m[r].y));
-          o = make_double2(__dsub_rn(f[r].x, m[r].x), __dsub_rn(f[r].y, m[r].y));
+          f[r] = make_double2(__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y));
+          m[r] = make_double2(__dsub_rn(a.x, b.x), __dsub_rn(a.y, b.y));
+        }
+      }
+      if (MIDFIX && mblock == 0) {            // rmid_s is zero beyond H, E / O are zero there too
+#pragma unroll
+        for (int r = 0; r < NPASS; ++r) {
+          const double rk = rmid_s[kc * BK + kr0 + 4 * r];
+          const double2 x = p.sign > 0 ? f[r] : m[r];
+          macc[r & 1][0] = __fma_rn(rk, x.x, macc[r & 1][0]);
+          macc[r & 1][1] = __fma_rn(rk, x.y, macc[r & 1][1]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NPASS; ++r) {
+        if (KCONTIG) {
+          *reinterpret_cast<double2*>(Et + sto + r * (16 * BK)) = f[r];       // 16 columns further: same parity
+          *reinterpret_cast<double2*>(Ot + sto + r * (16 * BK)) = m[r];
+        } else {
           const int kr = kr0 + 4 * r;
           const int so = kr * BN + (sto ^ (4 * ((kr >> 1) & 3)));
-          *reinterpret_cast<double2*>(Et + so) = e;
-          *reinterpret_cast<double2*>(Ot + so) = o;
-          if (MIDFIX && s_mblock == 0 && k0 + kr < H) {
-            const double rk = p.rmid[k0 + kr];
-            const double2 x = p.sign > 0 ? e : o;
-            macc0 = __fma_rn(rk, x.x, macc0);
-            macc1 = __fma_rn(rk, x.y, macc1);
-          }
+          *reinterpret_cast<double2*>(Et + so) = f[r];
+          *reinterpret_cast<double2*>(Ot + so) = m[r];
         }
+      }
+      // the last chunk of a tile that THIS group stages: its partial sums of the middle row ride with it
+      // (visible to the consumers once they have waited for the tile's later stages)
+      if (MIDFIX && mblock == 0 && kc + 2 >= nchunks) {
+        double* buf = midbuf + ((par * 2 + group) * 4 + kr0) * BN + sto;
+        *reinterpret_cast<double2*>(buf) = make_double2(__dadd_rn(macc[0][0], macc[1][0]), __dadd_rn(macc[0][1], macc[1][1]));
+        macc[0][0] = macc[0][1] = macc[1][0] = macc[1][1] = 0.0;
       }
       mbar_arrive(full + slot);
-      ++it;
-      if (++s_kc < nchunks) return;
-      // ---- end of a tile ---------------------------------------------------------------------------
-      if (MIDFIX && !KCONTIG) {
-        // middle row of an odd n: y[mid] = sum_k D[mid][k] X[k] + D[mid][mid] u[mid]; producer warp w
-        // holds the k rows = w (mod 4) of every column pair
-        double* buf = midbuf + ((s_tile / gridDim.x) & 1) * (3 * BN);
-        if (s_mblock == 0 && kr0 > 0) { buf[(kr0 - 1) * BN + sto] = macc0; buf[(kr0 - 1) * BN + sto + 1] = macc1; }
-        producer_sync();
-        const int64_t nn = (s_tile / p.m_blocks) * BN + sto;
-        if (s_mblock == 0 && kr0 == 0 && nn < p.NN) {
-          const double w0 = __dadd_rn(__dadd_rn(__dadd_rn(macc0, buf[sto]), buf[BN + sto]), buf[2 * BN + sto]);
-          const double w1 = __dadd_rn(__dadd_rn(__dadd_rn(macc1, buf[sto + 1]), buf[BN + sto + 1]), buf[2 * BN + sto + 1]);
-          const int64_t a = nn / p.before, b = nn - a * p.before;
-          const int64_t off = a * p.slab + b + int64_t(p.mid) * p.before;
-          const double2 um = ldg2(p.U + off);
-          const double dmm = p.rmid[nchunks * BK];
-          const double t0 = __fma_rn(dmm, um.x, w0), t1 = __fma_rn(dmm, um.y, w1);
-          double s0 = p.alpha, s1 = p.alpha;
-          if (p.scale_mode == PT_SCALE_AFTER) { s0 *= p.scale[a % p.scale_len]; s1 = s0; }
-          else if (p.scale_mode == PT_SCALE_BEFORE) { s0 *= p.scale[b]; s1 *= p.scale[b + 1]; }
-          else if (p.scale_mode == PT_SCALE_ROW) { const double sr = p.scale[p.mid]; s0 *= sr; s1 *= sr; }
-          double v0 = __dmul_rn(s0, t0), v1 = __dmul_rn(s1, t1);
-          if (p.beta != 0.0) {
-            const double2 o = *reinterpret_cast<const double2*>((SCAT ? p.C : p.Y) + off);
-            v0 = __fma_rn(p.beta, o.x, v0);
-            v1 = __fma_rn(p.beta, o.y, v1);
-          }
-          double* y;
-          if (SCAT) {
-            const int dq = p.mid / p.sc.chunk;
-            const int64_t q = a / p.sc.a_inner;
-            y = p.sc.base[dq] + int64_t(p.mid - dq * p.sc.chunk) * p.sc.s_i + p.sc.offset + q * p.sc.s_outer +
-                (a - q * p.sc.a_inner) * p.sc.s_inner + b;
-          } else {
-            y = p.Y + off;
-          }
-          *reinterpret_cast<double2*>(y) = make_double2(v0, v1);
-        }
-        macc0 = 0.0;
-        macc1 = 0.0;
-      }
-      s_kc = 0;
-      s_tile += gridDim.x;
-      s_mblock = int(s_tile % p.m_blocks);
-    };
-
-    double2 f0[NPASS], m0[NPASS], f1[NPASS], m1[NPASS];
-    l_setup(l_tile);
-    load(f0, m0);
-    for (int64_t i = 0; i < total_it; i += 2) {
-      if (i + 1 < total_it) load(f1, m1);
-      store(f0, m0);
-      if (i + 2 < total_it) load(f0, m0);
-      if (i + 1 < total_it) store(f1, m1);
+      // ---- two chunks further ---------------------------------------------------------------------------
+      it += 2;
+      advance();
+      advance();
+      if (it < total_it) load();
     }
     return;
   }
@@ -357,9 +356,17 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
 #pragma unroll
       for (int j = 0; j < WN; ++j) { acce[i][j][0] = acce[i][j][1] = 0.0; acco[i][j][0] = acco[i][j][1] = 0.0; }
 
+    const bool tracing = p.trace && tid == 0 && (tile / gridDim.x) < 16;
+    long long* tr = tracing ? p.trace + (int64_t(blockIdx.x) * 16 + tile / gridDim.x) * 8 : nullptr;
+    long long t_wait = 0;
+    if (tracing) tr[0] = clock64();                 // consumer starts the tile
     for (int kc = 0; kc < nchunks; ++kc, ++it) {
       const int slot = it % STAGES;
-      mbar_wait(full + slot, (it / STAGES) & 1u);
+      if (tracing) {
+        const long long t0 = clock64();
+        mbar_wait(full + slot, (it / STAGES) & 1u);
+        t_wait += clock64() - t0;
+      } else mbar_wait(full + slot, (it / STAGES) & 1u);
       const double* As = smem + size_t(slot) * STAGE;
       const double* Et = As + A_STAGE + b_off;
       const double* Ot = Et + B_TILE;
@@ -368,7 +375,41 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + slot);
     }
-    eo_epilogue<WR, WN, KCONTIG, true, SCAT, MIDFIX>(p, acce, acco, my_rt, rt0 * 8 + my_rt0 * 8, n0 + wn * WN * 8, g, t);
+    if (tracing) { tr[1] = clock64(); tr[3] = t_wait; }        // main loop done; cycles spent waiting for data
+    if (p.dbg == 3 && acce[0][0][0] != 12345.678) continue;      // timing experiment: no epilogue at all
+    if (MIDFIX && wm == 0 && m_block == 0 && lane < WN * 8) {
+      // y[mid] = sum_k D[mid][k] X[k] + D[mid][mid] u[mid]: the producers left eight partial sums per column
+      const int par = int((tile / gridDim.x) & 1);
+      const int col = wn * WN * 8 + lane;
+      const int64_t nn = n0 + col;
+      if (nn < p.NN) {
+        const double* mb = midbuf + par * PWARPS * BN + col;
+        double v = mb[0];
+#pragma unroll
+        for (int w = 1; w < PWARPS; ++w) v = __dadd_rn(v, mb[w * BN]);
+        v = __fma_rn(rmid_s[nchunks * BK], umid_s[par * BN + col], v);
+        const int64_t a = nn / p.before, b = nn - a * p.before;
+        double sc = p.alpha;
+        if (p.scale_mode == PT_SCALE_AFTER) sc *= p.scale[a % p.scale_len];
+        else if (p.scale_mode == PT_SCALE_BEFORE) sc *= p.scale[b];
+        else if (p.scale_mode == PT_SCALE_ROW) sc *= p.scale[p.mid];
+        double out = __dmul_rn(sc, v);
+        const int64_t off = a * p.slab + int64_t(p.mid) * p.before + b;
+        if (p.beta != 0.0) out = __fma_rn(p.beta, (SCAT ? p.C : p.Y)[off], out);
+        if (SCAT) {
+          const int dq = p.mid / p.sc.chunk;
+          const int64_t q = a / p.sc.a_inner;
+          p.sc.base[dq][int64_t(p.mid - dq * p.sc.chunk) * p.sc.s_i + p.sc.offset + q * p.sc.s_outer +
+                        (a - q * p.sc.a_inner) * p.sc.s_inner + b] = out;
+        } else {
+          p.Y[off] = out;
+        }
+      }
+    }
+    if (tracing) tr[7] = clock64();                              // middle row stored
+    eo_epilogue<WR, WN, KCONTIG, true, SCAT, MIDFIX>(p, acce, acco, my_rt, rt0 * 8 + my_rt0 * 8, n0 + wn * WN * 8, g, t,
+                                                     cmid_s, umid_s + ((tile / gridDim.x) & 1) * BN + wn * WN * 8);
+    if (tracing) tr[2] = clock64();                              // epilogue done
   }
 }
 
@@ -408,6 +449,7 @@ __global__ void pack_eo_ws_kernel(const double* __restrict__ D, int n, int H, in
 
 inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
 
+long long* g_ws_trace = nullptr;   // tuning hook: device buffer [grid][16 tiles][8] of clock64 stamps
 int g_ws_enabled = 1;      // tuning hook: pt_debug_set_eo_config(60 / 61) = never / default
 
 struct WsShape {
@@ -431,12 +473,13 @@ int launch_ws(EoParams& p, cudaStream_t stream) {
   int dev = 0;
   PT_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
+    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_MAX)));
     attr_set[dev] = true;
   }
   int64_t grid = pt::sm_count();
   if (grid > p.total_tiles) grid = p.total_tiles;
-  kern<<<unsigned(grid), NT, SMEM_BYTES, stream>>>(p);
+  const size_t smem_bytes = SMEM_FIXED + (MIDFIX ? size_t(p.MPH + p.KPH * 4 + 2) * sizeof(double) : 0);
+  kern<<<unsigned(grid), NT, smem_bytes, stream>>>(p);
   return pt::check_launch("pt_dense_apply_eo_ws");
 }
 
@@ -469,6 +512,7 @@ bool ws_eligible(int n, const double* U, const double* Y, const double* C, int64
   if (!aligned16(U)) return false;
   if (before == 1) return (n % 2) == 0;
   if (before % 2) return false;
+  if ((n & 1) && SMEM_FIXED + size_t(s.m_blocks * BMH + s.nchunks * BK + 2) * sizeof(double) > SMEM_MAX) return false;   // D[:, mid], D[mid, :] beside the ring
   if (map) {
     if ((map->s_outer | map->s_inner | map->s_i | map->offset) & 1) return false;
     return C == nullptr || aligned16(C);
@@ -499,7 +543,7 @@ int apply_ws_impl(const double* packed, int n, int sign, const double* U, double
   p.before = before; p.NN = after * before; p.slab = int64_t(n) * before;
   p.total_tiles = int64_t(s.m_blocks) * ((p.NN + BN - 1) / BN);
   p.alpha = alpha; p.beta = beta; p.scale_mode = scale_mode; p.scale_len = scale_len > 0 ? scale_len : 1;
-  p.cmid = nullptr; p.rmid = nullptr; p.dmm = 0.0; p.mid = -1;
+  p.cmid = nullptr; p.rmid = nullptr; p.dmm = 0.0; p.mid = -1; p.dbg = g_ws_enabled; p.trace = g_ws_trace;
   if (n & 1) {
     p.mid = (n - 1) / 2;
     p.cmid = packed + s.panels;
@@ -510,8 +554,13 @@ int apply_ws_impl(const double* packed, int n, int sign, const double* U, double
 
 }  // namespace
 
-extern "C" int pt_debug_set_eo_ws(int enabled) {
-  g_ws_enabled = enabled ? 1 : 0;
+extern "C" int pt_debug_set_eo_ws_trace(long long* device_buffer) {
+  g_ws_trace = device_buffer;
+  return PT_OK;
+}
+
+extern "C" int pt_debug_set_eo_ws(int mode) {      // 0 off, 1 default; 2 / 3: timing experiments (wrong results)
+  g_ws_enabled = mode;
   return PT_OK;
 }
 

@@ -30,17 +30,81 @@ struct EoParams {
   const double* __restrict__ rmid;  // rmid[k] = D[mid][k], k < H
   double dmm;                       // D[mid][mid]
   int mid;                          // (n-1)/2 when n is odd and the middle is split off, else -1
+  int dbg;                          // timing experiments only (pt_debug_set_eo_ws): 3 = no epilogue
+  long long* trace;                 // tuning hook (pt_debug_set_eo_ws_trace): per-CTA, per-tile clock64 stamps, or null
 };
 
 // Epilogue of one warp: acce/acco hold ze/zo for half-rows row0 + 8*i + g (i < my_rt) and columns
 // ncol0 + 8*j + 2*t + {0, 1}.  Rows i get ze + zo, rows n-1-i get s*(ze - zo).  MIDFIX: n is odd and
-// the middle column is not part of the half problem: ze += D[i][mid] * u[mid] first.
+// the middle column is not part of the half problem: ze += D[i][mid] * u[mid] first; cmid_s (the
+// column D[:, mid]) and umid_s (u[mid] of the tile's 64 columns, indexed by column - ncol_tile) then
+// come from shared memory (staged by the warp-specialised kernel), so no global load sits between
+// the accumulators and the stores.
 template <int WR, int WN, bool KCONTIG, bool VEC16, bool SCAT, bool MIDFIX>
 __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR][WN][2], double (&acco)[WR][WN][2],
-                                            int my_rt, int row0, int64_t ncol0, int g, int t) {
+                                            int my_rt, int row0, int64_t ncol0, int g, int t,
+                                            const double* cmid_s = nullptr, const double* umid_s = nullptr) {
   const int n = p.n;
   const bool use_beta = (p.beta != 0.0);
   const double sgn = double(p.sign);
+  // ---- interior tiles without scaling or scatter (the bulk of every large field): straight-line code,
+  // no per-element bounds checks, running pointers.  Same operations in the same order as the general
+  // path below, so the results are bit-identical.
+  // (an odd n whose middle row is part of the half problem — cp.async kernel — keeps the general path:
+  // there rows i and n-1-i coincide for i = mid)
+  if (!SCAT && (KCONTIG || VEC16) && (MIDFIX || (n & 1) == 0) && p.scale_mode == PT_SCALE_NONE && my_rt == WR &&
+      row0 + WR * 8 <= p.H && ncol0 + WN * 8 <= p.NN) {
+    const int64_t step = 8 * p.before;
+#pragma unroll
+    for (int j = 0; j < WN; ++j) {
+      const int64_t nn = ncol0 + j * 8 + 2 * t;
+      int64_t l0;
+      if (KCONTIG) {
+        l0 = nn * p.slab;
+      } else {
+        const int64_t a0 = nn / p.before;
+        l0 = a0 * p.slab + (nn - a0 * p.before);
+      }
+      double um0 = 0.0, um1 = 0.0;
+      if (MIDFIX) {
+        const double2 um = *reinterpret_cast<const double2*>(umid_s + (j * 8 + 2 * t));
+        um0 = um.x;
+        um1 = um.y;
+      }
+      double* ylo = p.Y + l0 + int64_t(row0 + g) * p.before;
+      double* yhi = p.Y + l0 + int64_t(n - 1 - row0 - g) * p.before;
+#pragma unroll
+      for (int i = 0; i < WR; ++i, ylo += step, yhi -= step) {
+        double e0 = acce[i][j][0], e1 = acce[i][j][1];
+        if (MIDFIX) {
+          const double cm = cmid_s[row0 + i * 8 + g];      // shared memory: no preloaded array (registers are tight)
+          e0 = __fma_rn(cm, um0, e0);
+          e1 = __fma_rn(cm, um1, e1);
+        }
+        double v0 = __dmul_rn(p.alpha, __dadd_rn(e0, acco[i][j][0]));
+        double v1 = __dmul_rn(p.alpha, __dadd_rn(e1, acco[i][j][1]));
+        double x0 = __dmul_rn(p.alpha, __dmul_rn(sgn, __dsub_rn(e0, acco[i][j][0])));
+        double x1 = __dmul_rn(p.alpha, __dmul_rn(sgn, __dsub_rn(e1, acco[i][j][1])));
+        if (KCONTIG) {          // columns nn and nn + 1 are n apart, rows contiguous
+          if (use_beta) {
+            v0 = __fma_rn(p.beta, ylo[0], v0); v1 = __fma_rn(p.beta, ylo[n], v1);
+            x0 = __fma_rn(p.beta, yhi[0], x0); x1 = __fma_rn(p.beta, yhi[n], x1);
+          }
+          ylo[0] = v0; ylo[n] = v1;
+          yhi[0] = x0; yhi[n] = x1;
+        } else {
+          if (use_beta) {
+            const double2 o = *reinterpret_cast<const double2*>(ylo), q = *reinterpret_cast<const double2*>(yhi);
+            v0 = __fma_rn(p.beta, o.x, v0); v1 = __fma_rn(p.beta, o.y, v1);
+            x0 = __fma_rn(p.beta, q.x, x0); x1 = __fma_rn(p.beta, q.y, x1);
+          }
+          *reinterpret_cast<double2*>(ylo) = make_double2(v0, v1);
+          *reinterpret_cast<double2*>(yhi) = make_double2(x0, x1);
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < WN; ++j) {
     const int64_t nn = ncol0 + j * 8 + 2 * t;
@@ -64,8 +128,9 @@ __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR
     const int64_t l0 = a0 * p.slab + b0, l1 = a1 * p.slab + b1;
     double um0 = 0.0, um1 = 0.0;
     if (MIDFIX) {
-      um0 = p.U[l0 + int64_t(p.mid) * p.before];
-      if (two) um1 = p.U[l1 + int64_t(p.mid) * p.before];
+      const double2 um = *reinterpret_cast<const double2*>(umid_s + (j * 8 + 2 * t));   // umid_s already at the warp's columns
+      um0 = um.x;
+      um1 = um.y;
     }
     int64_t d0 = 0, d1 = 0;
     if (SCAT) {
@@ -73,14 +138,18 @@ __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR
       d0 = p.sc.offset + q0 * p.sc.s_outer + (a0 - q0 * p.sc.a_inner) * p.sc.s_inner + b0;
       d1 = p.sc.offset + q1 * p.sc.s_outer + (a1 - q1 * p.sc.a_inner) * p.sc.s_inner + b1;
     }
+    // running offsets of rows i (upwards) and n-1-i (downwards): 8 rows per accumulator tile
+    int64_t off_lo = int64_t(row0 + g) * p.before;
+    int64_t off_hi = int64_t(n - 1 - row0 - g) * p.before;
+    const int64_t off_step = 8 * p.before;
 #pragma unroll
-    for (int i = 0; i < WR; ++i) {
+    for (int i = 0; i < WR; ++i, off_lo += off_step, off_hi -= off_step) {
       if (i >= my_rt) continue;
       const int hrow = row0 + i * 8 + g;
       if (hrow >= p.H) continue;
       double e0 = acce[i][j][0], e1 = acce[i][j][1];
       if (MIDFIX) {
-        const double cm = p.cmid[hrow];
+        const double cm = cmid_s[hrow];
         e0 = __fma_rn(cm, um0, e0);
         e1 = __fma_rn(cm, um1, e1);
       }
@@ -94,7 +163,7 @@ __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR
         double r0 = s0, r1 = s1;
         if (p.scale_mode == PT_SCALE_ROW) { const double sr = p.scale[row]; r0 *= sr; r1 *= sr; }
         double v0 = __dmul_rn(r0, w0), v1 = __dmul_rn(r1, w1);
-        const int64_t off = int64_t(row) * p.before;
+        const int64_t off = half == 0 ? off_lo : off_hi;
         const double* c0 = (SCAT ? p.C : p.Y) + l0 + off;
         const double* c1 = (SCAT ? p.C : p.Y) + l1 + off;
         double *y0, *y1;

@@ -93,7 +93,7 @@ def real_op(kind, n, order, npts, axis, batch, label):
     ops_mod.EVEN_ODD = True
 
 
-def eo_variants(kind, n, order, npts, axis, batch, label):
+def eo_variants(kind, n, order, npts, axis, batch, label, which=(True, False)):
     """Centrosymmetric operators: warp-specialised kernel vs the cp.async even-odd kernel."""
     import pytristan_b200.operators as ops_mod
     x = np.arange(n) * (2 * np.pi / n) if kind == "four" else pt.cheb(n, -1.0, 1.0)
@@ -104,7 +104,7 @@ def eo_variants(kind, n, order, npts, axis, batch, label):
     ring = [torch.randn(batch, P, dtype=torch.float64, device="cuda") for _ in range(max(1, min(4, int(6e8 // nb))))]
     Y = torch.empty_like(ring[0])
     fl = 2.0 * n * P * batch
-    for ws in (True, False):
+    for ws in which:
         ops_mod.EVEN_ODD_WS = ws
         i = [0]
 
@@ -122,9 +122,22 @@ def eo_variants(kind, n, order, npts, axis, batch, label):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "wsdbg":
+        lib = _lib.load()
+        for mode in (1, 3):
+            lib.pt_debug_set_eo_ws(mode)
+            print("== ws debug mode", mode, "(1 default, 3 no epilogue)")
+            eo_variants("four", 1024, 1, (1024, 257), 0, 64, "cfg2 d/dx FourMat K2 n=1024", (True,))
+            eo_variants("cheb", 257, 2, (1024, 257), 1, 64, "cfg2 d2/dy2 ChebMat K1 n=257", (True,))
+            eo_variants("cheb", 256, 2, (1024, 256), 1, 64, "n=256", (True,))
+            eo_variants("cheb", 2048, 1, (8192, 2048), 1, 1, "cfg5a-1/8 ChebMat K1 n=2048", (True,))
+            eo_variants("cheb", 512, 2, (512, 512, 512), 1, 1, "cfg5b y K1 n=512", (True,))
+        lib.pt_debug_set_eo_ws(1)
+        sys.exit(0)
     if what == "ws":
         eo_variants("four", 1024, 1, (1024, 257), 0, 64, "cfg2 d/dx FourMat K2 n=1024")
         eo_variants("cheb", 257, 2, (1024, 257), 1, 64, "cfg2 d2/dy2 ChebMat K1 n=257")
+        eo_variants("cheb", 256, 2, (1024, 256), 1, 64, "like cfg2 but n=256 (no middle row/column)")
         eo_variants("cheb", 512, 2, (1024, 512), 1, 64, "cfg3 radial K1 n=512 b64")
         eo_variants("four", 1024, 2, (1024, 512), 0, 64, "cfg3 azimuthal K2 n=1024 b64")
         eo_variants("cheb", 2048, 1, (8192, 2048), 1, 1, "cfg5a-1/8 ChebMat K1 n=2048")
