@@ -124,6 +124,49 @@ def test_config4_fd6_cube(n):
         err = float((out.view(n, n, n) - exact[k]).abs().max())
         assert err <= 2e-9, (k, err)          # rounding only: weights are O(n), values O(1)
     assert np.array_equal(ops[0].start, oracle.findiff_band(x, 1, 6)["start"])
+    del u, out, X, Y, Z, exact
+    torch.cuda.empty_cache()
+
+    # ---- oracle parity on a RANDOM field: sampled lines and planes, componentwise <= 1e-12 of |W||u| ------
+    # (hard part 6: the NumPy oracle cannot hold the whole cube; lines along the
+    # differentiated axis and planes containing it are independent problems it can)
+    gen = torch.Generator(device="cuda").manual_seed(1234 + n)
+    u = torch.randn(n ** 3, dtype=torch.float64, device="cuda", generator=gen)
+    out = torch.empty_like(u)
+    band = oracle.findiff_band(x, 1, 6)
+    absband = dict(band, W=np.abs(band["W"]))
+    rng = np.random.default_rng(n)
+    V, O = u.view(n, n, n), out.view(n, n, n)            # [z][y][x], x fastest
+    worst = 0.0
+    for k in range(3):
+        ops[k].apply(u, out=out)
+        # 48 random lines along axis k (+ the corner lines)
+        picks = [(0, 0), (n - 1, n - 1), (0, n - 1)] + [tuple(rng.integers(0, n, 2)) for _ in range(48)]
+        for (p, q) in picks:
+            sl = {0: (p, q, slice(None)), 1: (p, slice(None), q), 2: (slice(None), p, q)}[k]
+            line, got = V[sl].cpu().numpy(), O[sl].cpu().numpy()
+            ref = oracle.stencil_apply(band, line[None], (n,), 0)[0]
+            bound = oracle.stencil_apply(absband, np.abs(line)[None], (n,), 0)[0]
+            worst = max(worst, float(np.max(np.abs(got - ref) / bound)))
+        # two planes containing axis k: a 2-D grid problem for the oracle
+        for fixed in (int(rng.integers(0, n)), n - 1):
+            if k == 0:      # x-y plane at z = fixed: grid (nx, ny), axis 0
+                plane, got, npts2, ax = V[fixed].cpu().numpy(), O[fixed].cpu().numpy(), (n, n), 0
+            elif k == 1:    # x-y plane at z = fixed: axis 1
+                plane, got, npts2, ax = V[fixed].cpu().numpy(), O[fixed].cpu().numpy(), (n, n), 1
+            else:           # x-z plane at y = fixed: grid (nx, nz), axis 1
+                plane, got, npts2, ax = V[:, fixed, :].cpu().numpy(), O[:, fixed, :].cpu().numpy(), (n, n), 1
+            ref = oracle.stencil_apply(band, plane.reshape(1, -1), npts2, ax)
+            bound = oracle.stencil_apply(absband, np.abs(plane).reshape(1, -1), npts2, ax)
+            worst = max(worst, float(np.max(np.abs(got.reshape(1, -1) - ref) / bound)))
+    assert worst <= 1e-12, worst
+    # the fused one-read gradient against the three passes (another summation order: 1e-12 of max|y|)
+    outs = [torch.empty_like(u) for _ in range(3)] if _free_gb() > 4.0 * n ** 3 * 8 / 2 ** 30 else None
+    if outs is not None:
+        pt.gradient(ops, u, outs=outs)
+        for k in range(3):
+            ops[k].apply(u, out=out)
+            assert float((outs[k] - out).abs().max()) <= 1e-12 * float(out.abs().max()), k
 
 
 def test_config5a_cheb2048_batched():

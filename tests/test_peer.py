@@ -2,9 +2,9 @@
 
 CPU: the destination maps of the pencil redistributions (pt_scatter_map arithmetic restated in
 NumPy, all ranks emulated in one process) against the global transposed layouts.
-GPU: two worker processes sharing ONE GPU map each other's buffers through CUDA IPC and run the
-real kernels (scatter epilogue, peer scatter, halo loads, flag barrier); with >= 2 GPUs the same
-worker runs one rank per GPU."""
+GPU, one device: all ranks of the peer AND of the NCCL plans emulated in this process (threads, real
+kernels on real device buffers; tests/_emulated_fabric.py) — no kernel ever spins on another launch.
+GPU, >= 2 devices: one worker process per GPU over real CUDA IPC mappings and the device flag barrier."""
 import os
 import socket
 import subprocess
@@ -99,9 +99,9 @@ def test_scatter_maps_reproduce_the_pencil_layouts(py, pz, batch):
         np.testing.assert_array_equal(backA[r].reshape(want.shape), want)
 
 
-def _run_workers(world, same_gpu):
+def _run_workers(world):
     port = free_port()
-    procs = [subprocess.Popen([sys.executable, WORKER, str(r), str(world), str(port)] + (["same-gpu"] if same_gpu else []),
+    procs = [subprocess.Popen([sys.executable, WORKER, str(r), str(world), str(port)],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
     outs = []
     try:
@@ -117,8 +117,91 @@ def _run_workers(world, same_gpu):
 
 
 @pytest.mark.gpu
-def test_peer_paths_two_processes_one_gpu():
-    _run_workers(2, same_gpu=True)
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_paths_all_ranks_emulated_on_one_gpu(world):
+    """SURVEY 8e (ii)/(iii) on a 1-GPU box: every rank of the slab stencil, the fused slab gradient and the
+    pencil operator (scatter epilogue, pt_peer_scatter, way back) runs in this process — the real
+    kernels on real device buffers; only the CUDA IPC mapping and the flag barrier are replaced
+    (tests/_emulated_fabric.py) — against the oracle and, bit for bit, the single-device kernels."""
+    from _emulated_fabric import run_ranks
+    from _peer_checks import run_checks
+
+    failures = {}
+
+    def body(rank, w, fab):
+        failures[rank] = run_checks(rank, w, fab)
+
+    run_ranks(world, body)
+    assert all(not failures[r] for r in range(world)), failures
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("py,pz", [(2, 1), (1, 2), (2, 2), (4, 2)])
+def test_nccl_pencil_plan_all_ranks_emulated_on_one_gpu(py, pz):
+    """The pack -> all_to_all -> unpack form (PencilTranspose, pencil_apply_sum) with all ranks in this
+    process: pt_permute3d and the DMMA kernels are real, only all_to_all_single is replaced by copies
+    between the emulated ranks' buffers.  Result = the single-device sum, bit for bit, and the way back
+    (z_to_y, y_to_x) restores the layout."""
+    import threading
+
+    import torch
+
+    import pytristan_b200 as pt
+    import pytristan_b200.dist as D
+    from _emulated_fabric import current_rank, run_ranks
+
+    world = py * pz
+    NZ, NY, NX = 4 * pz, 6 * py * pz, 10 * py
+    rng = np.random.default_rng(7)
+    G = rng.standard_normal((NZ, NY, NX))
+    mats = [pt.ChebMat(pt.cheb(n), order=1 + (k % 2)) for k, n in enumerate((NX, NY, NZ))]
+    Gd = torch.from_numpy(G).cuda()
+    full = mats[0]._apply_device(Gd.reshape(-1), NZ * NY, NX, 1, None, 1.0, 0.0, None, None)
+    mats[1]._apply_device(Gd.reshape(-1), NZ, NY, NX, full, 1.0, 1.0, None, None)
+    mats[2]._apply_device(Gd.reshape(-1), 1, NZ, NY * NX, full, 1.0, 1.0, None, None)
+    full = full.view(NZ, NY, NX).cpu().numpy()
+
+    posted, host = {}, threading.Barrier(world)
+
+    def a2a(recv, send, group):          # group: the world ranks of the row / column, in order
+        me = current_rank()
+        idx, p = group.index(me), len(group)
+        posted[(tuple(group), me)] = send.reshape(-1)
+        host.wait()
+        chunk = send.numel() // p
+        out = recv.view(-1)
+        for j, src in enumerate(group):
+            out[j * chunk:(j + 1) * chunk].copy_(posted[(tuple(group), src)][idx * chunk:(idx + 1) * chunk])
+        host.wait()                      # everybody has read before the send buffers are reused
+
+    results = {}
+
+    def body(rank, w, fab):
+        ry, rz = rank % py, rank // py
+        row = [rz * py + y for y in range(py)]
+        col = [z * py + ry for z in range(pz)]
+        pen = D.PencilTranspose((NZ, NY, NX), py, pz, rank=rank, world=w, groups=(row, col))
+        u = torch.from_numpy(np.ascontiguousarray(G[rz * pen.nzl:(rz + 1) * pen.nzl, ry * pen.nyl:(ry + 1) * pen.nyl])).cuda()
+        res = D.pencil_apply_sum(mats, u, pen, back=False)
+        back = D.pencil_apply_sum(mats, u, pen, back=True)
+        results[rank] = (res.cpu().numpy(), back.cpu().numpy(), pen)
+
+    old = D.PencilTranspose._a2a
+    D.PencilTranspose._a2a = staticmethod(a2a)
+    try:
+        run_ranks(world, body)
+    except BaseException:
+        host.abort()
+        raise
+    finally:
+        D.PencilTranspose._a2a = old
+    for rank in range(world):
+        res, back, pen = results[rank]
+        ry, rz = rank % py, rank // py
+        slc = (slice(None), slice(rz * pen.nyl2, (rz + 1) * pen.nyl2), slice(ry * pen.nxl, (ry + 1) * pen.nxl))
+        assert np.array_equal(res.reshape(full[slc].shape), full[slc]), ("layout C", rank)
+        sla = (slice(rz * pen.nzl, (rz + 1) * pen.nzl), slice(ry * pen.nyl, (ry + 1) * pen.nyl), slice(None))
+        assert np.array_equal(back.reshape(full[sla].shape), full[sla]), ("layout A", rank)
 
 
 @pytest.mark.gpu
@@ -128,4 +211,4 @@ def test_peer_paths_one_rank_per_gpu():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs 2 GPUs")
-    _run_workers(4 if n >= 4 else 2, same_gpu=False)
+    _run_workers(4 if n >= 4 else 2)
