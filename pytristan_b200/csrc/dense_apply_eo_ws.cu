@@ -211,8 +211,9 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
         int64_t la = 0;
         if (nn < p.NN) {
           ok = 0xfu;
-          const int64_t a = nn / p.before;
-          la = a * p.slab + (nn - a * p.before);
+          int64_t a, b;
+          split_column(nn, p.before, a, b);
+          la = a * p.slab + b;
         }
         fwd = p.U + la + int64_t(kr0) * p.before;
         mir = p.U + la + int64_t(n - 1 - kr0) * p.before;
@@ -384,11 +385,12 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
       const int64_t nn = n0 + col;
       if (nn < p.NN) {
         const double* mb = midbuf + par * PWARPS * BN + col;
-        double v = mb[0];
-#pragma unroll
-        for (int w = 1; w < PWARPS; ++w) v = __dadd_rn(v, mb[w * BN]);
+        // fixed pairwise order (a chain of 7 dependent DADDs is ~2x the latency of the 3-level tree)
+        double v = __dadd_rn(__dadd_rn(__dadd_rn(mb[0], mb[BN]), __dadd_rn(mb[2 * BN], mb[3 * BN])),
+                             __dadd_rn(__dadd_rn(mb[4 * BN], mb[5 * BN]), __dadd_rn(mb[6 * BN], mb[7 * BN])));
         v = __fma_rn(rmid_s[nchunks * BK], umid_s[par * BN + col], v);
-        const int64_t a = nn / p.before, b = nn - a * p.before;
+        int64_t a, b;
+        split_column(nn, p.before, a, b);
         double sc = p.alpha;
         if (p.scale_mode == PT_SCALE_AFTER) sc *= p.scale[a % p.scale_len];
         else if (p.scale_mode == PT_SCALE_BEFORE) sc *= p.scale[b];

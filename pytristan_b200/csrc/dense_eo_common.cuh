@@ -34,6 +34,17 @@ struct EoParams {
   long long* trace;                 // tuning hook (pt_debug_set_eo_ws_trace): per-CTA, per-tile clock64 stamps, or null
 };
 
+// column index nn -> (a, b) = (nn / before, nn % before): 32-bit division when it fits (a 64-bit
+// division is ~10x the instructions and sits on the critical path of every tile's epilogue)
+__device__ __forceinline__ void split_column(int64_t nn, int64_t before, int64_t& a, int64_t& b) {
+  if ((uint64_t(nn) | uint64_t(before)) >> 32) {
+    a = nn / before;
+  } else {
+    a = int64_t(uint32_t(nn) / uint32_t(before));
+  }
+  b = nn - a * before;
+}
+
 // Epilogue of one warp: acce/acco hold ze/zo for half-rows row0 + 8*i + g (i < my_rt) and columns
 // ncol0 + 8*j + 2*t + {0, 1}.  Rows i get ze + zo, rows n-1-i get s*(ze - zo).  MIDFIX: n is odd and
 // the middle column is not part of the half problem: ze += D[i][mid] * u[mid] first; cmid_s (the
@@ -47,23 +58,33 @@ __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR
   const int n = p.n;
   const bool use_beta = (p.beta != 0.0);
   const double sgn = double(p.sign);
-  // ---- interior tiles without scaling or scatter (the bulk of every large field): straight-line code,
-  // no per-element bounds checks, running pointers.  Same operations in the same order as the general
+  // ---- interior tiles without scatter (the bulk of every large field): straight-line code, no
+  // per-element bounds checks, running pointers.  Same operations in the same order as the general
   // path below, so the results are bit-identical.
   // (an odd n whose middle row is part of the half problem — cp.async kernel — keeps the general path:
   // there rows i and n-1-i coincide for i = mid)
-  if (!SCAT && (KCONTIG || VEC16) && (MIDFIX || (n & 1) == 0) && p.scale_mode == PT_SCALE_NONE && my_rt == WR &&
-      row0 + WR * 8 <= p.H && ncol0 + WN * 8 <= p.NN) {
+  if (!SCAT && (KCONTIG || VEC16) && (MIDFIX || (n & 1) == 0) && my_rt == WR && row0 + WR * 8 <= p.H &&
+      ncol0 + WN * 8 <= p.NN) {
     const int64_t step = 8 * p.before;
+    const bool row_scale = p.scale_mode == PT_SCALE_ROW;
 #pragma unroll
     for (int j = 0; j < WN; ++j) {
       const int64_t nn = ncol0 + j * 8 + 2 * t;
-      int64_t l0;
+      int64_t l0, a0, b0;
       if (KCONTIG) {
+        a0 = nn; b0 = 0;
         l0 = nn * p.slab;
       } else {
-        const int64_t a0 = nn / p.before;
-        l0 = a0 * p.slab + (nn - a0 * p.before);
+        split_column(nn, p.before, a0, b0);
+        l0 = a0 * p.slab + b0;
+      }
+      double s0 = p.alpha, s1 = p.alpha;                  // column nn, column nn + 1
+      if (p.scale_mode == PT_SCALE_AFTER) {
+        s0 *= p.scale[a0 % p.scale_len];
+        s1 = KCONTIG ? p.alpha * p.scale[(a0 + 1) % p.scale_len] : s0;     // K1: both columns in one slab
+      } else if (p.scale_mode == PT_SCALE_BEFORE) {
+        s0 *= p.scale[b0];
+        s1 *= p.scale[KCONTIG ? 0 : b0 + 1];
       }
       double um0 = 0.0, um1 = 0.0;
       if (MIDFIX) {
@@ -81,10 +102,15 @@ __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR
           e0 = __fma_rn(cm, um0, e0);
           e1 = __fma_rn(cm, um1, e1);
         }
-        double v0 = __dmul_rn(p.alpha, __dadd_rn(e0, acco[i][j][0]));
-        double v1 = __dmul_rn(p.alpha, __dadd_rn(e1, acco[i][j][1]));
-        double x0 = __dmul_rn(p.alpha, __dmul_rn(sgn, __dsub_rn(e0, acco[i][j][0])));
-        double x1 = __dmul_rn(p.alpha, __dmul_rn(sgn, __dsub_rn(e1, acco[i][j][1])));
+        double rl0 = s0, rl1 = s1, rh0 = s0, rh1 = s1;
+        if (row_scale) {
+          const double sl = p.scale[row0 + i * 8 + g], sh = p.scale[n - 1 - row0 - i * 8 - g];
+          rl0 *= sl; rl1 *= sl; rh0 *= sh; rh1 *= sh;
+        }
+        double v0 = __dmul_rn(rl0, __dadd_rn(e0, acco[i][j][0]));
+        double v1 = __dmul_rn(rl1, __dadd_rn(e1, acco[i][j][1]));
+        double x0 = __dmul_rn(rh0, __dmul_rn(sgn, __dsub_rn(e0, acco[i][j][0])));
+        double x1 = __dmul_rn(rh1, __dmul_rn(sgn, __dsub_rn(e1, acco[i][j][1])));
         if (KCONTIG) {          // columns nn and nn + 1 are n apart, rows contiguous
           if (use_beta) {
             v0 = __fma_rn(p.beta, ylo[0], v0); v1 = __fma_rn(p.beta, ylo[n], v1);
@@ -114,7 +140,7 @@ __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR
     if (KCONTIG) {
       a0 = nn; b0 = 0; a1 = nn + 1; b1 = 0;
     } else {
-      a0 = nn / p.before; b0 = nn - a0 * p.before;
+      split_column(nn, p.before, a0, b0);
       if (b0 + 1 < p.before) { a1 = a0; b1 = b0 + 1; } else { a1 = a0 + 1; b1 = 0; }
     }
     double s0 = p.alpha, s1 = p.alpha;

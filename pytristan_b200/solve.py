@@ -44,7 +44,7 @@ def with_rows(op, rows, new_rows):
         raise ValueError("rows must be unique")
     new = np.ascontiguousarray(new_rows, dtype=np.float64).reshape(rows.size, n)
     d_rows = torch.from_numpy(rows.astype(np.int32)).cuda()
-    d_new = torch.from_numpy(new).cuda()
+    d_new = _lib.to_device(new)
     _lib.check(_lib.load().pt_replace_rows(_lib.dptr(d_mat), n, _lib.dptr(d_rows), int(rows.size), _lib.dptr(d_new),
                                            _lib.stream_ptr()), "pt_replace_rows")
     npts = getattr(op, "npts", None) or (n,)
