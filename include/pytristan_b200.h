@@ -287,6 +287,14 @@ int pt_dense_apply_eo_scatter(const double* packed_even, const double* packed_od
 int pt_dense_apply_eo_ws_scatter(const double* packed_ws, int n, int sign, const double* U, const double* C,
                                  int64_t after, int64_t before, double alpha, double beta,
                                  const pt_scatter_map* map, pt_stream_t stream);
+/* ... and the redistribution of the FIELD fused into the same kernel: besides alpha * (D U) + beta * C through
+ * `map`, U itself is stored through `field_map` by the warps that load it (every element of U passes through
+ * their registers exactly once), so that a pencil transposition of (field, running sum) is ONE kernel whose NVLink
+ * traffic is spread under its main loop — no pt_peer_scatter pass.  PT_ERR_UNSUPPORTED as pt_dense_apply_eo_ws,
+ * and for field maps with odd strides / chunk. */
+int pt_dense_apply_eo_ws_scatter_copy(const double* packed_ws, int n, int sign, const double* U, const double* C,
+                                      int64_t after, int64_t before, double alpha, double beta,
+                                      const pt_scatter_map* map, const pt_scatter_map* field_map, pt_stream_t stream);
 /* The same redistribution for an array that is only moved (the field itself): 16-byte peer
  * stores, no staging buffer, no pack/unpack pass.  before == 1 requires s_i == 1. */
 int pt_peer_scatter(const double* src, int n, int64_t after, int64_t before,

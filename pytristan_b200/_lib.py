@@ -93,6 +93,8 @@ SIGNATURES = {
                                       _c_ptr, _c_i32, _c_i64, _c_ptr]),
     "pt_dense_apply_eo_ws_scatter": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64,
                                               _c_f64, ctypes.POINTER(ScatterMap), _c_ptr]),
+    "pt_dense_apply_eo_ws_scatter_copy": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64,
+                                                   _c_f64, ctypes.POINTER(ScatterMap), ctypes.POINTER(ScatterMap), _c_ptr]),
     "pt_fourier_twiddles": (_c_i32, [_c_i32, _c_ptr, _c_ptr]),
     "pt_fourier_apply": (_c_i32, [_c_ptr, _c_i32, _c_f64, _c_i32, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_f64, _c_f64,
                                   _c_ptr, _c_i64, _c_ptr]),

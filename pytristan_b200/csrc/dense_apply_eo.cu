@@ -487,6 +487,7 @@ int apply_eo_impl(const double* pe, const double* po, int n, int sign, const dou
   p.alpha = alpha; p.beta = beta; p.scale_mode = scale_mode; p.scale_len = scale_len > 0 ? scale_len : 1;
   p.m_blocks = 1; p.rt_per_block = 1; p.total_tiles = 0;
   p.cmid = nullptr; p.rmid = nullptr; p.dmm = 0.0; p.mid = -1; p.dbg = 0; p.trace = nullptr;
+  p.cp = ScatterDev{nullptr, 1, 1, 0, 0, 0, 0};
   cudaStream_t st = pt::as_stream(stream);
   if (before == 1) {
     const bool vec = (n % 2 == 0) && aligned16(U);

@@ -23,6 +23,11 @@
 //     chain waits for the FP64 pipe behind the DMMAs at every link); the eight partial sums of a column
 //     travel through shared memory with the tile's last chunk and the epilogue adds and stores them.
 //     (Accumulating in the consumer warps was measured: the DFMAs stall the DMMA stream, 0.24 vs 0.19 ms.)
+//   * COPY (pencil redistribution): the producers of the first row block also store the field tiles
+//     they load — every element of U passes through their registers exactly once — through a second
+//     scatter map into the peers' buffers.  The redistribution of the FIELD then needs no kernel of its
+//     own (this CTA shape leaves no room on an SM for a concurrent copy kernel): its NVLink traffic is
+//     spread under the whole main loop, like that of the result, which leaves through the epilogue.
 //
 // One CTA per SM (192 KB ring of 4 stages), persistent over tiles (m fastest).
 #include "dense_eo_common.cuh"
@@ -145,7 +150,17 @@ struct WsDispatch<0, KCONTIG> {
                                              const int (&)[WN], double (&)[WR][WN][2], double (&)[WR][WN][2]) {}
 };
 
-template <bool KCONTIG, bool SCAT, bool MIDFIX>
+// destination of element (a, i, b) under a scatter map: the (a, b) part and the i part separately
+__device__ __forceinline__ int64_t map_a_part(const ScatterDev& m, int64_t a, int64_t b) {
+  const int64_t q = ((uint64_t(a) | uint64_t(m.a_inner)) >> 32) ? a / m.a_inner : int64_t(uint32_t(a) / uint32_t(m.a_inner));
+  return m.offset + q * m.s_outer + (a - q * m.a_inner) * m.s_inner + b;
+}
+__device__ __forceinline__ double* map_i_part(const ScatterDev& m, int i) {
+  const int q = i / m.chunk;
+  return m.base[q] + int64_t(i - q * m.chunk) * m.s_i;
+}
+
+template <bool KCONTIG, bool SCAT, bool MIDFIX, bool COPY>
 __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams p) {
   extern __shared__ __align__(128) double smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + SMEM_RING);
@@ -280,6 +295,36 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
       }
       if (MIDFIX && kc == 0 && kr0 == 0)      // u[mid] of the tile's columns for the consumers' epilogue
         *reinterpret_cast<double2*>(umid_s + par * BN + sto) = um;
+      if (COPY && mblock == 0) {
+        // the field itself, redistributed: forward pieces cover rows i < H, mirrored pieces rows i >= n - H
+        const int k0 = kc * BK;
+        const int64_t n0 = (tile / p.m_blocks) * BN;
+        if (KCONTIG) {
+          const int kf = k0 + c2, km = n - 2 - kf;           // s_i == 1 on the contiguous axis
+          double* df = map_i_part(p.cp, kf);
+          double* dm = map_i_part(p.cp, km);
+#pragma unroll
+          for (int r = 0; r < NPASS; ++r)
+            if (((ok >> r) & 1u) && kf < H) {
+              const int64_t ao = map_a_part(p.cp, n0 + colp + 16 * r, 0);
+              *reinterpret_cast<double2*>(df + ao) = f[r];
+              *reinterpret_cast<double2*>(dm + ao) = m[r];
+            }
+        } else if (ok) {
+          int64_t a, b;
+          split_column(n0 + sto, p.before, a, b);
+          const int64_t ao = map_a_part(p.cp, a, b);
+#pragma unroll
+          for (int r = 0; r < NPASS; ++r) {
+            const int kr = k0 + kr0 + 4 * r;
+            if (kr < H) {
+              *reinterpret_cast<double2*>(map_i_part(p.cp, kr) + ao) = f[r];
+              *reinterpret_cast<double2*>(map_i_part(p.cp, n - 1 - kr) + ao) = m[r];
+            }
+          }
+          if (MIDFIX && kc == 0 && kr0 == 0) *reinterpret_cast<double2*>(map_i_part(p.cp, p.mid) + ao) = um;
+        }
+      }
       // all FP64 work of the chunk in one burst (in place: E over f, O over m)
 #pragma unroll
       for (int r = 0; r < NPASS; ++r) {
@@ -468,9 +513,9 @@ WsShape ws_shape(int n) {
   return s;
 }
 
-template <bool KCONTIG, bool SCAT, bool MIDFIX>
+template <bool KCONTIG, bool SCAT, bool MIDFIX, bool COPY = false>
 int launch_ws(EoParams& p, cudaStream_t stream) {
-  auto kern = dense_apply_eo_ws_kernel<KCONTIG, SCAT, MIDFIX>;
+  auto kern = dense_apply_eo_ws_kernel<KCONTIG, SCAT, MIDFIX, COPY>;
   static bool attr_set[64] = {false};
   int dev = 0;
   PT_CUDA(cudaGetDevice(&dev));
@@ -489,8 +534,12 @@ int launch_ws(EoParams& p, cudaStream_t stream) {
 
 namespace ptdense {
 
-int launch_eo_ws(EoParams& p, bool kcontig, bool scatter, cudaStream_t stream) {
+int launch_eo_ws(EoParams& p, bool kcontig, bool scatter, bool copy, cudaStream_t stream) {
   const bool mid = p.mid >= 0;
+  if (copy) {          // result through the scatter epilogue AND the field itself through the producers
+    if (kcontig) return mid ? PT_ERR_UNSUPPORTED : launch_ws<true, true, false, true>(p, stream);
+    return mid ? launch_ws<false, true, true, true>(p, stream) : launch_ws<false, true, false, true>(p, stream);
+  }
   if (kcontig) {
     if (mid) return PT_ERR_UNSUPPORTED;
     return scatter ? launch_ws<true, true, false>(p, stream) : launch_ws<true, false, false>(p, stream);
@@ -505,13 +554,18 @@ namespace {
 
 // shapes the warp-specialised kernel covers; everything else runs dense_apply_eo.cu
 bool ws_eligible(int n, const double* U, const double* Y, const double* C, int64_t after, int64_t before,
-                 const pt_scatter_map* map) {
+                 const pt_scatter_map* map, const pt_scatter_map* copy_map) {
   if (!g_ws_enabled || n < 128) return false;
   const WsShape s = ws_shape(n);
   const int64_t NN = after * before;
   const int64_t tiles = int64_t(s.m_blocks) * ((NN + BN - 1) / BN);
   if (tiles < pt::sm_count()) return false;            // small fields: the small-tile cp.async kernel fills the GPU better
   if (!aligned16(U)) return false;
+  if (copy_map) {      // 16-byte stores of the field pieces: even strides, pieces never straddle two destinations
+    if ((copy_map->s_outer | copy_map->s_inner | copy_map->offset | copy_map->chunk) & 1) return false;
+    if (before > 1 && (copy_map->s_i & 1)) return false;
+    if (before == 1 && copy_map->s_i != 1) return false;
+  }
   if (before == 1) return (n % 2) == 0;
   if (before % 2) return false;
   if ((n & 1) && SMEM_FIXED + size_t(s.m_blocks * BMH + s.nchunks * BK + 2) * sizeof(double) > SMEM_MAX) return false;   // D[:, mid], D[mid, :] beside the ring
@@ -524,7 +578,7 @@ bool ws_eligible(int n, const double* U, const double* Y, const double* C, int64
 
 int apply_ws_impl(const double* packed, int n, int sign, const double* U, double* Y, const double* C, int64_t after,
                   int64_t before, double alpha, double beta, const double* scale, int scale_mode, int64_t scale_len,
-                  const pt_scatter_map* map, pt_stream_t stream) {
+                  const pt_scatter_map* map, const pt_scatter_map* copy_map, pt_stream_t stream) {
   PT_REQUIRE(packed && U, "pt_dense_apply_eo_ws: null pointer");
   PT_REQUIRE(n >= 2, "pt_dense_apply_eo_ws: n=%d", n);
   PT_REQUIRE(sign == 1 || sign == -1, "pt_dense_apply_eo_ws: sign must be +1 or -1");
@@ -532,13 +586,16 @@ int apply_ws_impl(const double* packed, int n, int sign, const double* U, double
   PT_REQUIRE(scale_mode >= PT_SCALE_NONE && scale_mode <= PT_SCALE_BEFORE, "pt_dense_apply_eo_ws: bad scale_mode %d", scale_mode);
   PT_REQUIRE(scale_mode == PT_SCALE_NONE || scale != nullptr, "pt_dense_apply_eo_ws: scale is null");
   PT_REQUIRE(scale_mode != PT_SCALE_AFTER || scale_len > 0, "pt_dense_apply_eo_ws: scale_len must be > 0");
-  if (!ws_eligible(n, U, Y, C, after, before, map)) return PT_ERR_UNSUPPORTED;
+  if (!ws_eligible(n, U, Y, C, after, before, map, copy_map)) return PT_ERR_UNSUPPORTED;
   if (after == 0) return PT_OK;
   const WsShape s = ws_shape(n);
   EoParams p;
   p.Dpe = packed; p.Dpo = nullptr; p.U = U; p.Y = Y; p.C = C; p.scale = scale;
   p.sc = map ? ScatterDev{map->base, map->chunk, map->a_inner, map->s_outer, map->s_inner, map->s_i, map->offset}
              : ScatterDev{nullptr, 1, 1, 0, 0, 0, 0};
+  p.cp = copy_map ? ScatterDev{copy_map->base, copy_map->chunk, copy_map->a_inner, copy_map->s_outer, copy_map->s_inner,
+                               copy_map->s_i, copy_map->offset}
+                  : ScatterDev{nullptr, 1, 1, 0, 0, 0, 0};
   p.n = n; p.H = s.H; p.MPH = s.m_blocks * BMH; p.KPH = s.nchunks * 4;
   p.rt_per_block = BMH / 8; p.m_blocks = s.m_blocks;
   p.sign = sign;
@@ -551,7 +608,7 @@ int apply_ws_impl(const double* packed, int n, int sign, const double* U, double
     p.cmid = packed + s.panels;
     p.rmid = p.cmid + int64_t(s.m_blocks) * BMH;
   }
-  return launch_eo_ws(p, before == 1, map != nullptr, pt::as_stream(stream));
+  return launch_eo_ws(p, before == 1, map != nullptr, copy_map != nullptr, pt::as_stream(stream));
 }
 
 }  // namespace
@@ -589,7 +646,7 @@ extern "C" int pt_dense_apply_eo_ws(const double* packed_ws, int n, int sign, co
   PT_REQUIRE(Y != nullptr, "pt_dense_apply_eo_ws: null pointer");
   PT_REQUIRE(U != Y, "pt_dense_apply_eo_ws: in-place application is not supported");
   return apply_ws_impl(packed_ws, n, sign, U, Y, Y, after, before, alpha, beta, scale, scale_mode, scale_len, nullptr,
-                       stream);
+                       nullptr, stream);
 }
 
 extern "C" int pt_dense_apply_eo_ws_scatter(const double* packed_ws, int n, int sign, const double* U, const double* C,
@@ -601,5 +658,20 @@ extern "C" int pt_dense_apply_eo_ws_scatter(const double* packed_ws, int n, int 
   PT_REQUIRE(map->a_inner >= 1, "pt_dense_apply_eo_ws_scatter: a_inner must be >= 1");
   PT_REQUIRE(beta == 0.0 || C != nullptr, "pt_dense_apply_eo_ws_scatter: beta != 0 needs C");
   return apply_ws_impl(packed_ws, n, sign, U, nullptr, C ? C : U, after, before, alpha, beta, nullptr, PT_SCALE_NONE, 0,
-                       map, stream);
+                       map, nullptr, stream);
+}
+
+extern "C" int pt_dense_apply_eo_ws_scatter_copy(const double* packed_ws, int n, int sign, const double* U,
+                                                 const double* C, int64_t after, int64_t before, double alpha,
+                                                 double beta, const pt_scatter_map* map, const pt_scatter_map* field_map,
+                                                 pt_stream_t stream) {
+  PT_REQUIRE(map && map->base && field_map && field_map->base, "pt_dense_apply_eo_ws_scatter_copy: null map");
+  for (const pt_scatter_map* m : {map, field_map}) {
+    PT_REQUIRE(m->nranks >= 1 && m->chunk >= 1 && int64_t(m->chunk) * m->nranks >= n,
+               "pt_dense_apply_eo_ws_scatter_copy: %d destinations x %d rows do not cover n=%d", m->nranks, m->chunk, n);
+    PT_REQUIRE(m->a_inner >= 1, "pt_dense_apply_eo_ws_scatter_copy: a_inner must be >= 1");
+  }
+  PT_REQUIRE(beta == 0.0 || C != nullptr, "pt_dense_apply_eo_ws_scatter_copy: beta != 0 needs C");
+  return apply_ws_impl(packed_ws, n, sign, U, nullptr, C ? C : U, after, before, alpha, beta, nullptr, PT_SCALE_NONE, 0,
+                       map, field_map, stream);
 }

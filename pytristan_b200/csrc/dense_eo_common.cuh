@@ -15,6 +15,7 @@ struct EoParams {
   const double* __restrict__ C;     // beta input (== Y unless scattering)
   const double* __restrict__ scale;
   ScatterDev sc;
+  ScatterDev cp;                    // warp-specialised kernel, COPY: second map through which U itself is redistributed
   int n, H;                         // operator size; half size (rows and k of the half problem)
   int MPH, KPH;                     // padded half rows, k-panels of the half problem (KPH is even)
   int rt_per_block, m_blocks;       // row-tiles (8 half-rows) per tile, tiles along the half-rows
@@ -218,6 +219,6 @@ __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR
 
 // entry point of the warp-specialised kernel (dense_apply_eo_ws.cu); returns PT_ERR_UNSUPPORTED,
 // without a message and without doing anything, for shapes it does not cover
-int launch_eo_ws(EoParams& p, bool kcontig, bool scatter, cudaStream_t stream);
+int launch_eo_ws(EoParams& p, bool kcontig, bool scatter, bool copy, cudaStream_t stream);
 
 }  // namespace ptdense

@@ -394,13 +394,15 @@ class PencilPeer(PencilTranspose):
     Four symmetric buffers of the local block size hold the field and the running sum in layouts
     B and C.  ``apply_sum`` is then, per rank and with no collective call:
 
-        side stream : u            --pt_peer_scatter-->          peers' uB      (overlaps the Dx kernel)
-        main stream : Dx u         --scatter epilogue-->         peers' accB
+        ONE kernel  : Dx u         --scatter epilogue-->         peers' accB
+                      u            --stored by the loading warps-> peers' uB    (pt_dense_apply_eo_ws_scatter_copy)
         barrier
-        side stream : uB           --pt_peer_scatter-->          peers' uC      (overlaps the Dy kernel)
-        main stream : Dy uB + accB --scatter epilogue-->         peers' accC
+        ONE kernel  : Dy uB + accB --scatter epilogue-->         peers' accC
+                      uB           --stored by the loading warps-> peers' uC
         barrier
         main stream : accC += Dz uC                                              (local)
+
+    (shapes the warp-specialised kernel declines move the field with ``pt_peer_scatter`` instead)
     """
 
     def __init__(self, shape, py, pz, fabric, batch=1):
@@ -469,22 +471,30 @@ class PencilPeer(PencilTranspose):
         side = self._side
         lead = self.batch * self.nzl
         u = u.reshape(-1)
-        # ---- A -> B
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            _lib.check(lib.pt_peer_scatter(_lib.dptr(u), self.nx, lead * self.nyl, 1,
-                                           ctypes.byref(self.maps["u_AB"]), _lib.stream_ptr()), "pt_peer_scatter")
-        dx._apply_scatter(u, lead * self.nyl, self.nx, 1, None, 1.0, 0.0, self.maps["acc_AB"])
-        main.wait_stream(side)
+        # ---- A -> B: Dx u leaves through the scatter epilogue; u itself rides in the same kernel (stored by
+        # the warps that load it) when the warp-specialised kernel covers the shape, else it is moved by
+        # pt_peer_scatter on a side stream that only waits for what preceded the DMMA kernel
+        ready = torch.cuda.Event()
+        ready.record(main)
+        if not dx._apply_scatter(u, lead * self.nyl, self.nx, 1, None, 1.0, 0.0, self.maps["acc_AB"],
+                                 field_map=self.maps["u_AB"]):
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                _lib.check(lib.pt_peer_scatter(_lib.dptr(u), self.nx, lead * self.nyl, 1,
+                                               ctypes.byref(self.maps["u_AB"]), _lib.stream_ptr()), "pt_peer_scatter")
+            main.wait_stream(side)
         fab.barrier()
         # ---- B -> C
         uB, accB = self.uB.local, self.accB.local
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            _lib.check(lib.pt_peer_scatter(_lib.dptr(uB), self.ny, lead, self.nxl,
-                                           ctypes.byref(self.maps["u_BC"]), _lib.stream_ptr()), "pt_peer_scatter")
-        dy._apply_scatter(uB, lead, self.ny, self.nxl, accB, 1.0, 1.0, self.maps["acc_BC"])
-        main.wait_stream(side)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        if not dy._apply_scatter(uB, lead, self.ny, self.nxl, accB, 1.0, 1.0, self.maps["acc_BC"],
+                                 field_map=self.maps["u_BC"]):
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                _lib.check(lib.pt_peer_scatter(_lib.dptr(uB), self.ny, lead, self.nxl,
+                                               ctypes.byref(self.maps["u_BC"]), _lib.stream_ptr()), "pt_peer_scatter")
+            main.wait_stream(side)
         fab.barrier()
         # ---- C: local
         dz._apply_device(self.uC.local, self.batch, self.nz, self.nyl2 * self.nxl, self.accC.local, 1.0, 1.0,

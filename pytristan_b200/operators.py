@@ -132,6 +132,8 @@ def _field_to_device(u):
 # half-size tensor-core products.  Set EVEN_ODD = False to force the plain kernel.
 EVEN_ODD = True
 EVEN_ODD_WS = True          # large fields: the warp-specialised even-odd kernel (csrc/dense_apply_eo_ws.cu)
+FUSED_FIELD_COPY = True     # pencil redistributions: the field rides in the DMMA kernel (pt_dense_apply_eo_ws_scatter_copy)
+STATS = {"fused_field_copies": 0}       # how often that happened (tests and bench.py report it)
 EO_TOLERANCE = 4.0e-15
 
 
@@ -332,18 +334,31 @@ class _DiffMat(np.ndarray):
         )
         return d_y
 
-    def _apply_scatter(self, d_u, after, n, before, c, alpha, beta, smap):
+    def _apply_scatter(self, d_u, after, n, before, c, alpha, beta, smap, field_map=None):
         """``alpha * D u + beta * c`` stored through the pencil-redistribution map ``smap``
-        (``pt_dense_apply_scatter``: the epilogue writes into the peers' buffers)."""
+        (``pt_dense_apply_scatter``: the epilogue writes into the peers' buffers).  With ``field_map`` the
+        field ``u`` itself is redistributed through that second map BY THE SAME KERNEL when the
+        warp-specialised kernel covers the shape (``pt_dense_apply_eo_ws_scatter_copy``); returns True
+        in that case, False when the caller still has to move ``u`` (``pt_peer_scatter``)."""
         lib = _lib.load()
         eo = self._eo_forms() if EVEN_ODD else None
         if eo is not None:
             if eo[3] is not None and EVEN_ODD_WS:
+                if field_map is not None and FUSED_FIELD_COPY:
+                    rc = lib.pt_dense_apply_eo_ws_scatter_copy(_lib.dptr(eo[3]), n, eo[0], _lib.dptr(d_u), _lib.dptr(c),
+                                                               after, before, float(alpha), float(beta),
+                                                               ctypes.byref(smap), ctypes.byref(field_map),
+                                                               _lib.stream_ptr())
+                    if rc == 0:
+                        STATS["fused_field_copies"] += 1
+                        return True
+                    if rc != -3:
+                        _lib.check(rc, "pt_dense_apply_eo_ws_scatter_copy")
                 rc = lib.pt_dense_apply_eo_ws_scatter(_lib.dptr(eo[3]), n, eo[0], _lib.dptr(d_u), _lib.dptr(c), after,
                                                       before, float(alpha), float(beta), ctypes.byref(smap),
                                                       _lib.stream_ptr())
                 if rc == 0:
-                    return
+                    return False
                 if rc != -3:
                     _lib.check(rc, "pt_dense_apply_eo_ws_scatter")
             _lib.check(
@@ -352,13 +367,14 @@ class _DiffMat(np.ndarray):
                                               ctypes.byref(smap), _lib.stream_ptr()),
                 "pt_dense_apply_eo_scatter",
             )
-            return
+            return False
         _lib.check(
             lib.pt_dense_apply_scatter(_lib.dptr(self._packed_device()), n, n, _lib.dptr(d_u), _lib.dptr(c),
                                        after, before, float(alpha), float(beta), ctypes.byref(smap),
                                        _lib.stream_ptr()),
             "pt_dense_apply_scatter",
         )
+        return False
 
     def matmul(self, other):
         """``D @ other``.

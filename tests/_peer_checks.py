@@ -130,4 +130,36 @@ def run_checks(rank, world, fab):
                 failures.append(("pencil_peer != single-device bits", py, pz, batch))
             fab.barrier()
 
+    # ---- pencils large enough for the warp-specialised kernel: the field redistribution is fused into
+    # the DMMA kernel (pt_dense_apply_eo_ws_scatter_copy); same bits as the single-device kernels -------------
+    if world == 2:
+        import pytristan_b200.operators as ops_mod
+
+        for (py, pz) in ((2, 1), (1, 2)):
+            NZ, NY, NX = 128, 256, 256
+            G = rng.standard_normal((1, NZ, NY, NX))
+            mats = [pt.ChebMat(pt.cheb(n), order=1 + (k % 2)) for k, n in enumerate((NX, NY, NZ))]
+            pp = D.PencilPeer((NZ, NY, NX), py, pz, fab, batch=1)
+            ry, rz = rank % py, rank // py
+            u = torch.from_numpy(np.ascontiguousarray(
+                G[:, rz * pp.nzl:(rz + 1) * pp.nzl, ry * pp.nyl:(ry + 1) * pp.nyl, :])).cuda()
+            before_count = ops_mod.STATS["fused_field_copies"]
+            for rep in range(2):
+                res = pp.apply_sum(mats, u).cpu().numpy()
+            fab.check()
+            fused = ops_mod.STATS["fused_field_copies"] - before_count
+            if torch.cuda.get_device_properties(0).multi_processor_count <= 148 and fused < 2:
+                failures.append(("large pencil: the field copy was not fused", py, pz, fused))
+            Gd = torch.from_numpy(G).cuda()
+            full = mats[0]._apply_device(Gd.reshape(-1), NZ * NY, NX, 1, None, 1.0, 0.0, None, None)
+            mats[1]._apply_device(Gd.reshape(-1), NZ, NY, NX, full, 1.0, 1.0, None, None)
+            mats[2]._apply_device(Gd.reshape(-1), 1, NZ, NY * NX, full, 1.0, 1.0, None, None)
+            sl = (slice(None), slice(None), slice(rz * pp.nyl2, (rz + 1) * pp.nyl2), slice(ry * pp.nxl, (ry + 1) * pp.nxl))
+            if not np.array_equal(full.view(1, NZ, NY, NX).cpu().numpy()[sl], res):
+                failures.append(("large pencil (fused field copy) != single-device bits", py, pz))
+            # the moved field itself: layout C holds u
+            uC = pp.uC.local.view(1, NZ, pp.nyl2, pp.nxl).cpu().numpy()
+            if not np.array_equal(uC, G[sl]):
+                failures.append(("large pencil: redistributed field differs", py, pz))
+            fab.barrier()
     return failures

@@ -229,3 +229,48 @@ def test_ws_scatter_epilogue_matches_the_cp_async_scatter():
             bound = 1.5 * oracle.abs_bound(D, U[None], (before, n, after), 1)[0] + 0.25 * np.abs(c.cpu().numpy())
             assert np.max(np.abs((outs[0] - outs[1])[32:32 + U.size].cpu().numpy()) / bound) <= TOL
         assert float(outs[0][:32].abs().max()) == 0.0 and float(outs[0][32 + u.numel():].abs().max()) == 0.0
+
+
+def test_ws_fused_field_copy_redistributes_the_field_bit_for_bit():
+    """pt_dense_apply_eo_ws_scatter_copy: besides the result (scatter epilogue) the producers store the field
+    itself through a second map.  Single-destination maps here; the pencil maps over several ranks are
+    covered by tests/test_peer.py (emulated ranks) and, with >= 2 GPUs, by the real fabric."""
+    import torch
+
+    from pytristan_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    for (n, after, before, sign) in [(256, 9500, 1, 1), (260, 4801, 1, -1), (256, 4, 2400, -1), (257, 4, 2400, 1),
+                                     (130, 160, 62, 1), (385, 3, 1600, -1)]:
+        D = _sym(rng, n, sign)
+        _, pe, po, pw = _forms(D, sign)
+        gen = torch.Generator(device="cuda").manual_seed(n + before)
+        u = torch.randn(after * n * before, dtype=torch.float64, device="cuda", generator=gen)
+        total = u.numel()
+
+        def maps(dest_y, dest_u):
+            out = []
+            for dest, off in ((dest_y, 32), (dest_u, 6)):
+                table = torch.tensor([dest.data_ptr()], dtype=torch.int64, device="cuda")
+                m = _lib.ScatterMap()
+                m.nranks, m.chunk = 1, n + (n & 1)            # an even chunk that covers n
+                m.a_inner, m.s_outer, m.s_inner, m.s_i, m.offset = 1, n * before, 0, before, off
+                m.base = table.data_ptr()
+                m._keep = table
+                out.append(m)
+            return out
+
+        y1 = torch.zeros(total + 64, dtype=torch.float64, device="cuda")
+        c1 = torch.full((total + 64,), float("nan"), dtype=torch.float64, device="cuda")
+        my, mu = maps(y1, c1)
+        rc = lib.pt_dense_apply_eo_ws_scatter_copy(_lib.dptr(pw), n, sign, _lib.dptr(u), None, after, before, 1.0, 0.0,
+                                                   ctypes.byref(my), ctypes.byref(mu), _lib.stream_ptr())
+        assert rc == 0, (n, after, before)
+        assert torch.equal(c1[6:6 + total], u), ("field copy", n, after, before)      # every element, exactly once or same value
+        assert torch.isnan(c1[:6]).all() and torch.isnan(c1[6 + total:]).all()
+        y2 = torch.zeros(total + 64, dtype=torch.float64, device="cuda")
+        my2, _ = maps(y2, c1)
+        assert lib.pt_dense_apply_eo_ws_scatter(_lib.dptr(pw), n, sign, _lib.dptr(u), None, after, before, 1.0, 0.0,
+                                                ctypes.byref(my2), _lib.stream_ptr()) == 0
+        assert torch.equal(y1, y2), ("result unchanged by the fused copy", n, after, before)
