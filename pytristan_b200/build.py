@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libpytristan_b200.so")
-SOURCES = ["common.cu", "dense_apply.cu", "dense_apply_tma.cu", "stencil.cu", "generators.cu", "peer.cu", "fourier_fft.cu", "solve.cu", "dense_apply_eo.cu", "dense_apply_eo_ws.cu"]
+SOURCES = ["common.cu", "dense_apply.cu", "stencil.cu", "generators.cu", "peer.cu", "fourier_fft.cu", "solve.cu", "dense_apply_eo.cu", "dense_apply_eo_ws.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC",

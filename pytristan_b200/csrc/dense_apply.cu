@@ -387,7 +387,6 @@ int launch_cfg(DenseParams& p, cudaStream_t stream) {
 
 int g_dense_config = -1;  // tuning hook (pt_debug_set_dense_config); -1 = choose by shape
 int g_dense_atma = 0;     // tuning hook (pt_debug_set_dense_tma(2)): operator panels via cp.async.bulk
-int g_dense_tma = 0;      // tuning hook (pt_debug_set_dense_tma): 1 = persistent TMA/mbarrier kernel
 
 // CTAs the large tiles would launch: below one per SM the GPU is mostly idle (single fields:
 // BASELINE config 3 at B = 1), so the small 64x32 tile (config 2) is used to fill it
@@ -428,13 +427,8 @@ inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr
 
 }  // namespace
 
-namespace ptdense {
-int launch_tma(DenseParams& p, bool kcontig, int cfg, cudaStream_t stream);
-}
-
 extern "C" int pt_debug_set_dense_tma(int mode) {
-  g_dense_tma = (mode == 1);   // 1: persistent mbarrier kernel
-  g_dense_atma = (mode == 2);  // 2: cp.async kernel with bulk-copied operator panels
+  g_dense_atma = (mode == 2);  // 2: cp.async kernel with bulk-copied operator panels (A/B timing; bit-identical)
   return PT_OK;
 }
 
@@ -497,17 +491,9 @@ extern "C" int pt_dense_apply(const double* packed, int n_out, int n_in, const d
   cudaStream_t st = pt::as_stream(stream);
   if (before == 1) {
     const bool vec = (n_in % 2 == 0) && aligned16(U);
-    if (vec && g_dense_tma) {
-      const int rc = ptdense::launch_tma(p, true, choose_config(p), st);
-      if (rc != PT_ERR_UNSUPPORTED) return rc;
-    }
     return vec ? launch_shape<true, true>(p, st) : launch_shape<true, false>(p, st);
   }
   const bool vec = (before % 2 == 0) && aligned16(U) && aligned16(Y);
-  if (vec && g_dense_tma) {
-    const int rc = ptdense::launch_tma(p, false, choose_config(p), st);
-    if (rc != PT_ERR_UNSUPPORTED) return rc;
-  }
   return vec ? launch_shape<false, true>(p, st) : launch_shape<false, false>(p, st);
 }
 

@@ -1,5 +1,5 @@
-// Shared device helpers of the dense-apply kernels (cp.async kernel: dense_apply.cu; TMA/mbarrier
-// persistent kernel: dense_apply_tma.cu).
+// Shared device helpers of the dense-apply kernels (plain operators: dense_apply.cu; centrosymmetric
+// operators: dense_apply_eo.cu and the warp-specialised dense_apply_eo_ws.cu).
 #pragma once
 #include "common.cuh"
 

@@ -68,6 +68,8 @@ __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR
       ncol0 + WN * 8 <= p.NN) {
     const int64_t step = 8 * p.before;
     const bool row_scale = p.scale_mode == PT_SCALE_ROW;
+    const bool unit = p.scale_mode == PT_SCALE_NONE && p.alpha == 1.0;
+    const bool pos = p.sign > 0;
 #pragma unroll
     for (int j = 0; j < WN; ++j) {
       const int64_t nn = ncol0 + j * 8 + 2 * t;
@@ -108,10 +110,17 @@ __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR
           const double sl = p.scale[row0 + i * 8 + g], sh = p.scale[n - 1 - row0 - i * 8 - g];
           rl0 *= sl; rl1 *= sl; rh0 *= sh; rh1 *= sh;
         }
-        double v0 = __dmul_rn(rl0, __dadd_rn(e0, acco[i][j][0]));
-        double v1 = __dmul_rn(rl1, __dadd_rn(e1, acco[i][j][1]));
-        double x0 = __dmul_rn(rh0, __dmul_rn(sgn, __dsub_rn(e0, acco[i][j][0])));
-        double x1 = __dmul_rn(rh1, __dmul_rn(sgn, __dsub_rn(e1, acco[i][j][1])));
+        // FP64 instructions are expensive here: whatever a warp issues on the FP64 pipe queues behind the
+        // DMMAs of the warps that are still (or again) in their main loop.  So: the sign of the mirrored
+        // rows is an operand swap (o - e = -(e - o) exactly), and alpha = 1 without scaling multiplies nothing.
+        const double o0 = acco[i][j][0], o1 = acco[i][j][1];
+        double v0 = __dadd_rn(e0, o0), v1 = __dadd_rn(e1, o1);
+        double x0 = pos ? __dsub_rn(e0, o0) : __dsub_rn(o0, e0);
+        double x1 = pos ? __dsub_rn(e1, o1) : __dsub_rn(o1, e1);
+        if (!unit) {
+          v0 = __dmul_rn(rl0, v0); v1 = __dmul_rn(rl1, v1);
+          x0 = __dmul_rn(rh0, x0); x1 = __dmul_rn(rh1, x1);
+        }
         if (KCONTIG) {          // columns nn and nn + 1 are n apart, rows contiguous
           if (use_beta) {
             v0 = __fma_rn(p.beta, ylo[0], v0); v1 = __fma_rn(p.beta, ylo[n], v1);
