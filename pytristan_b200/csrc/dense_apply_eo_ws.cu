@@ -21,7 +21,7 @@
 //     the epilogue (one FMA per element), the middle ROW is a dot product the producers accumulate
 //     from the E (or O) values they form anyway (two independent DFMA chains per thread: a dependent
 //     chain waits for the FP64 pipe behind the DMMAs at every link); the eight partial sums of a column
-//     travel through shared memory with the tile's last chunk and the epilogue adds and stores them.
+//     meet in shared memory and the producer group that stages the tile's last chunk adds and stores them.
 //     (Accumulating in the consumer warps was measured: the DFMAs stall the DMMA stream, 0.24 vs 0.19 ms.)
 //   * COPY (pencil redistribution): the producers of the first row block also store the field tiles
 //     they load — every element of U passes through their registers exactly once — through a second
@@ -46,6 +46,7 @@ constexpr int BMH = CW_M * WR * 8;                      // 128 half-rows per til
 constexpr int BN = CW_N * WN * 8;                       // 64 columns per tile
 constexpr int BK = 16;                                  // k per chunk = 2 panel pairs
 constexpr int STAGES = 4;
+constexpr int STAGGER = 2;                              // chunks by which the second consumer row half trails the first
 constexpr int A_PAIR = 2 * BMH * 8;                     // doubles of one panel pair: [e|o][128][8]
 constexpr int A_STAGE = 2 * A_PAIR;                     // 4096 doubles = 32 KB
 constexpr int B_TILE = BN * BK;                         // 1024 doubles = 8 KB (E tile; O tile follows)
@@ -79,6 +80,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+// non-blocking probe of a phase (the blocking form above may suspend the warp)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
   asm volatile(
@@ -358,14 +373,55 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
           *reinterpret_cast<double2*>(Ot + so) = m[r];
         }
       }
-      // the last chunk of a tile that THIS group stages: its partial sums of the middle row ride with it
-      // (visible to the consumers once they have waited for the tile's later stages)
-      if (MIDFIX && mblock == 0 && kc + 2 >= nchunks) {
+      // the last chunk of a tile that THIS group stages: its partial sums of the middle row go to shared memory
+      const bool mid_last = MIDFIX && mblock == 0 && kc + 2 >= nchunks;
+      if (mid_last) {
         double* buf = midbuf + ((par * 2 + group) * 4 + kr0) * BN + sto;
         *reinterpret_cast<double2*>(buf) = make_double2(__dadd_rn(macc[0][0], macc[1][0]), __dadd_rn(macc[0][1], macc[1][1]));
         macc[0][0] = macc[0][1] = macc[1][0] = macc[1][1] = 0.0;
       }
       mbar_arrive(full + slot);
+      if (mid_last && kc == nchunks - 1) {
+        // ... and the group that stages the tile's LAST chunk finishes the row:
+        //   y[mid] = sum_k D[mid][k] X[k] + D[mid][mid] u[mid]
+        // Its own four warps meet at a named barrier; the other group's partial sums (written before it
+        // arrived on the previous chunk's full barrier) and u[mid] (written with chunk 0) are visible once
+        // that phase has completed.  The producers have the slack for this (the consumers do not:
+        // finishing the row in their epilogue cost 2.3 K cycles of a 43 K-cycle tile).
+        if (group == 0) asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        else asm volatile("bar.sync 2, 128;\n" ::: "memory");
+        if (kr0 == 0 && ok) {
+          mbar_wait(full + (it - 1) % STAGES, ((it - 1) / STAGES) & 1u);
+          const double* mb = midbuf + par * PWARPS * BN + sto;
+          double2 v[PWARPS];
+#pragma unroll
+          for (int w = 0; w < PWARPS; ++w) v[w] = *reinterpret_cast<const double2*>(mb + w * BN);
+          // fixed pairwise order
+          double w0 = __dadd_rn(__dadd_rn(__dadd_rn(v[0].x, v[1].x), __dadd_rn(v[2].x, v[3].x)),
+                                __dadd_rn(__dadd_rn(v[4].x, v[5].x), __dadd_rn(v[6].x, v[7].x)));
+          double w1 = __dadd_rn(__dadd_rn(__dadd_rn(v[0].y, v[1].y), __dadd_rn(v[2].y, v[3].y)),
+                                __dadd_rn(__dadd_rn(v[4].y, v[5].y), __dadd_rn(v[6].y, v[7].y)));
+          const double2 umv = *reinterpret_cast<const double2*>(umid_s + par * BN + sto);
+          const double dmm = rmid_s[nchunks * BK];
+          w0 = __fma_rn(dmm, umv.x, w0);
+          w1 = __fma_rn(dmm, umv.y, w1);
+          int64_t a, b;
+          split_column((tile / p.m_blocks) * BN + sto, p.before, a, b);
+          double s0 = p.alpha, s1 = p.alpha;
+          if (p.scale_mode == PT_SCALE_AFTER) { s0 *= p.scale[a % p.scale_len]; s1 = s0; }
+          else if (p.scale_mode == PT_SCALE_BEFORE) { s0 *= p.scale[b]; s1 *= p.scale[b + 1]; }
+          else if (p.scale_mode == PT_SCALE_ROW) { const double sr = p.scale[p.mid]; s0 *= sr; s1 *= sr; }
+          double o0 = __dmul_rn(s0, w0), o1 = __dmul_rn(s1, w1);
+          const int64_t off = a * p.slab + int64_t(p.mid) * p.before + b;
+          if (p.beta != 0.0) {
+            const double2 c = *reinterpret_cast<const double2*>((SCAT ? p.C : p.Y) + off);
+            o0 = __fma_rn(p.beta, c.x, o0);
+            o1 = __fma_rn(p.beta, c.y, o1);
+          }
+          double* y = SCAT ? map_i_part(p.sc, p.mid) + map_a_part(p.sc, a, b) : p.Y + off;
+          *reinterpret_cast<double2*>(y) = make_double2(o0, o1);
+        }
+      }
       // ---- two chunks further ---------------------------------------------------------------------------
       it += 2;
       advance();
@@ -386,6 +442,13 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
   const int b_off = KCONTIG ? ((wn * WN * 8 + g) * BK + 2 * t) : (2 * t * BN);
   const int frag_swz = KCONTIG ? (g & 1) : 0;
   unsigned it = 0;
+  bool ready = false;
+  // The two consumer warps of a sub-partition (one per row half) would otherwise reach every tile's
+  // epilogue together and leave the DMMA pipe idle for its whole duration.  The second row half starts two
+  // chunks late (it waits for chunk 2 to land before it touches chunk 0); the offset then sustains itself:
+  // while one warp stores, the other has the pipe to itself.  tuning hook: pt_debug_set_eo_ws(6) = no stagger
+  if (wm == 1 && p.dbg != 6 && nchunks * ((p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) > STAGGER)
+    mbar_wait(full + STAGGER, 0);
   for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const int m_block = int(tile % p.m_blocks);
     const int64_t n0 = (tile / p.m_blocks) * BN;
@@ -408,11 +471,16 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
     if (tracing) tr[0] = clock64();                 // consumer starts the tile
     for (int kc = 0; kc < nchunks; ++kc, ++it) {
       const int slot = it % STAGES;
-      if (tracing) {
-        const long long t0 = clock64();
-        mbar_wait(full + slot, (it / STAGES) & 1u);
-        t_wait += clock64() - t0;
-      } else mbar_wait(full + slot, (it / STAGES) & 1u);
+      // `ready` was probed while the previous chunk's DMMAs were issuing: the round trip to the barrier
+      // unit (~100 cycles even when the phase has completed) is off the critical path
+      if (!ready) {
+        if (tracing) {
+          const long long t0 = clock64();
+          mbar_wait(full + slot, (it / STAGES) & 1u);
+          t_wait += clock64() - t0;
+        } else mbar_wait(full + slot, (it / STAGES) & 1u);
+      }
+      ready = mbar_test(full + (it + 1) % STAGES, ((it + 1) / STAGES) & 1u);   // next stage (a later phase can not complete early)
       const double* As = smem + size_t(slot) * STAGE;
       const double* Et = As + A_STAGE + b_off;
       const double* Ot = Et + B_TILE;
@@ -423,36 +491,6 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
     }
     if (tracing) { tr[1] = clock64(); tr[3] = t_wait; }        // main loop done; cycles spent waiting for data
     if (p.dbg == 3 && acce[0][0][0] != 12345.678) continue;      // timing experiment: no epilogue at all
-    if (MIDFIX && wm == 0 && m_block == 0 && lane < WN * 8) {
-      // y[mid] = sum_k D[mid][k] X[k] + D[mid][mid] u[mid]: the producers left eight partial sums per column
-      const int par = int((tile / gridDim.x) & 1);
-      const int col = wn * WN * 8 + lane;
-      const int64_t nn = n0 + col;
-      if (nn < p.NN) {
-        const double* mb = midbuf + par * PWARPS * BN + col;
-        // fixed pairwise order (a chain of 7 dependent DADDs is ~2x the latency of the 3-level tree)
-        double v = __dadd_rn(__dadd_rn(__dadd_rn(mb[0], mb[BN]), __dadd_rn(mb[2 * BN], mb[3 * BN])),
-                             __dadd_rn(__dadd_rn(mb[4 * BN], mb[5 * BN]), __dadd_rn(mb[6 * BN], mb[7 * BN])));
-        v = __fma_rn(rmid_s[nchunks * BK], umid_s[par * BN + col], v);
-        int64_t a, b;
-        split_column(nn, p.before, a, b);
-        double sc = p.alpha;
-        if (p.scale_mode == PT_SCALE_AFTER) sc *= p.scale[a % p.scale_len];
-        else if (p.scale_mode == PT_SCALE_BEFORE) sc *= p.scale[b];
-        else if (p.scale_mode == PT_SCALE_ROW) sc *= p.scale[p.mid];
-        double out = __dmul_rn(sc, v);
-        const int64_t off = a * p.slab + int64_t(p.mid) * p.before + b;
-        if (p.beta != 0.0) out = __fma_rn(p.beta, (SCAT ? p.C : p.Y)[off], out);
-        if (SCAT) {
-          const int dq = p.mid / p.sc.chunk;
-          const int64_t q = a / p.sc.a_inner;
-          p.sc.base[dq][int64_t(p.mid - dq * p.sc.chunk) * p.sc.s_i + p.sc.offset + q * p.sc.s_outer +
-                        (a - q * p.sc.a_inner) * p.sc.s_inner + b] = out;
-        } else {
-          p.Y[off] = out;
-        }
-      }
-    }
     if (tracing) tr[7] = clock64();                              // middle row stored
     eo_epilogue<WR, WN, KCONTIG, true, SCAT, MIDFIX>(p, acce, acco, my_rt, rt0 * 8 + my_rt0 * 8, n0 + wn * WN * 8, g, t,
                                                      cmid_s, umid_s + ((tile / gridDim.x) & 1) * BN + wn * WN * 8);

@@ -86,8 +86,32 @@ def apply_host(ops, fields, outs=None, chunk_fields=None):
     u_flat = u.view(-1)
     outs_flat = [o.view(-1) for o in outs_t]
 
-    cf = chunk_fields or max(1, -(-nfields // 16))   # ~16 chunks: measured best on PCIe Gen5 (tools/e2e_sweep.py)
-    nchunks = -(-nfields // cf)
+    # chunk schedule: a list of field counts, or one count for uniform chunks.  Default: a short ramp
+    # (1, 1, 2, 4, ... fields) so that the device-to-host stream — the long pole: it carries one output per
+    # operator — starts after ~0.1 ms instead of after a full-size chunk, then chunks of nfields/8
+    # (few, large copies: every chunk boundary costs the copy engines an event round trip);
+    # tools/e2e_sweep.py measures the alternatives
+    if chunk_fields is None:
+        big = max(1, -(-nfields // 8))
+        sched, step, left = [], 1, nfields
+        while left > 0:
+            take = min(step, big, left)
+            sched.append(take)
+            left -= take
+            if len(sched) >= 2:
+                step *= 2
+    elif isinstance(chunk_fields, (list, tuple)):
+        sched = [int(c) for c in chunk_fields]
+        if any(c < 1 for c in sched) or sum(sched) != nfields:
+            raise ValueError("apply_host: the chunk schedule must be positive and sum to the number of fields")
+    else:
+        cf1 = max(1, int(chunk_fields))
+        sched = [cf1] * (nfields // cf1) + ([nfields % cf1] if nfields % cf1 else [])
+    nchunks = len(sched)
+    cf = max(sched)
+    starts = [0]
+    for c in sched:
+        starts.append(starts[-1] + c)
     cur = torch.cuda.current_stream()
     s_in, s_out = _copy_streams(torch)
     slots = min(2, nchunks)
@@ -100,8 +124,7 @@ def apply_host(ops, fields, outs=None, chunk_fields=None):
     s_out.wait_stream(cur)
     for c in range(nchunks):
         slot = c % slots
-        lo = c * cf
-        hi = min(nfields, lo + cf)
+        lo, hi = starts[c], starts[c + 1]
         cnt = (hi - lo) * total
         with torch.cuda.stream(s_in):
             if c >= slots:

@@ -130,9 +130,9 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what == "wsdbg":
         lib = _lib.load()
-        for mode in (1, 3):
+        for mode in (1, 6, 1, 6):
             lib.pt_debug_set_eo_ws(mode)
-            print("== ws debug mode", mode, "(1 default, 3 no epilogue)")
+            print("== ws debug mode", mode, "(1 default, 6 no consumer stagger)")
             eo_variants("four", 1024, 1, (1024, 257), 0, 64, "cfg2 d/dx FourMat K2 n=1024", (True,))
             eo_variants("cheb", 257, 2, (1024, 257), 1, 64, "cfg2 d2/dy2 ChebMat K1 n=257", (True,))
             eo_variants("cheb", 256, 2, (1024, 256), 1, 64, "n=256", (True,))
