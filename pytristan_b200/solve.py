@@ -10,7 +10,9 @@ hot path in a collocation solver built on these matrices).
                                       on the device (``pt_invert``, Gauss-Jordan with partial
                                       pivoting); each solve is then the hot path itself —
                                       ``pt_dense_apply`` with the inverse, all lines at once, no
-                                      transposes.
+                                      transposes — optionally followed by steps of iterative refinement
+                                      (residual with ``A``, correction with the inverse: two more passes
+                                      each) that bring the residual to the backward-stable level.
 """
 import ctypes
 
@@ -65,12 +67,18 @@ def dirichlet(op):
 class AxisSolver:
     """``A y = f`` along one grid axis, for every grid line of a batch of fields.
 
-    ``AxisSolver(A, npts=None, axis=None)``: ``A`` is an ``n x n`` matrix (ndarray or operator; an
-    operator supplies ``npts``/``axis``).  ``solve(f)`` accepts what ``apply`` accepts.  Raises
+    ``AxisSolver(A, npts=None, axis=None, refine=0)``: ``A`` is an ``n x n`` matrix (ndarray or operator;
+    an operator supplies ``npts``/``axis``).  ``solve(f)`` accepts what ``apply`` accepts.  Raises
     ``numpy.linalg.LinAlgError`` when ``A`` is singular.
+
+    ``refine`` steps of iterative refinement follow the product with the inverse, each two more passes of
+    the hot path: ``r = f - A y`` (``pt_dense_apply`` with alpha = -1, beta = 1) and ``y += A^-1 r``.  One
+    step brings the residual of an ill-conditioned collocation system (cond ~ n^4) from
+    ``cond * eps * |f|`` down to the backward-stable level ``eps * |A| |y|`` — what an LU solve with
+    refinement delivers — without leaving the tensor cores or transposing anything.
     """
 
-    def __init__(self, A, npts=None, axis=None):
+    def __init__(self, A, npts=None, axis=None, refine=0):
         torch = _lib.require_cuda()
         lib = _lib.load()
         d_a, n = _device_matrix(A)
@@ -92,8 +100,28 @@ class AxisSolver:
         if step:
             raise np.linalg.LinAlgError(f"AxisSolver: singular matrix (elimination step {step - 1})")
         self.n, self.npts, self.axis = n, tuple(int(v) for v in npts), int(axis)
+        self.refine = int(refine)
+        if self.refine < 0:
+            raise ValueError("AxisSolver: refine must be >= 0")
         self.inverse = _DiffMat._wrap(d_inv, self.npts, self.axis, None, None)
+        self.matrix = _DiffMat._wrap(d_a, self.npts, self.axis, None, None)      # for the residuals
 
-    def solve(self, f, out=None):
-        """``y`` with ``A y[.., :, ..] = f[.., :, ..]`` along the axis (same kind and shape as ``f``)."""
-        return self.inverse.apply(f, out=out)
+    def solve(self, f, out=None, refine=None):
+        """``y`` with ``A y[.., :, ..] = f[.., :, ..]`` along the axis (same kind and shape as ``f``);
+        ``refine`` overrides the number of refinement steps given to the constructor."""
+        steps = self.refine if refine is None else int(refine)
+        if steps <= 0:
+            return self.inverse.apply(f, out=out)
+        from .operators import _field_to_device
+
+        d_f, kind = _field_to_device(f)
+        after, n, before = self.inverse._split(d_f.numel())
+        d_y = self.inverse._apply_device(d_f, after, n, before, out, 1.0, 0.0, None, None)
+        d_r = _lib.empty((d_f.numel(),))
+        for _ in range(steps):
+            d_r.copy_(d_f.reshape(-1))
+            self.matrix._apply_device(d_y.reshape(-1), after, n, before, d_r, -1.0, 1.0, None, None)     # r = f - A y
+            self.inverse._apply_device(d_r, after, n, before, d_y.reshape(-1), 1.0, 1.0, None, None)      # y += A^-1 r
+        if kind == "numpy":
+            return d_y.cpu().numpy().reshape(np.shape(f))
+        return d_y.view(d_f.shape)

@@ -88,3 +88,40 @@ def test_helmholtz_along_each_axis_of_a_3d_grid(axis):
     cond = np.linalg.cond(A)
     assert np.max(np.abs(y - ref)) <= 1e-13 * cond * np.max(np.abs(ref))
     assert np.max(np.abs(back - F)) <= 1e-12 * cond * np.max(np.abs(F))
+
+
+@pytest.mark.parametrize("n", [129, 257])
+def test_iterative_refinement_reaches_the_backward_stable_residual(n):
+    """Chebyshev Poisson operator with Dirichlet rows (cond ~ n^4): the product with the explicit inverse
+    leaves a residual ~ cond * eps; one refinement step (r = f - A y, y += A^-1 r: two more DMMA passes)
+    brings it to ~ eps * |A| |y|, like an LU solve with refinement."""
+    import torch
+
+    import pytristan_b200 as pt
+
+    x = pt.cheb(n, -1.0, 1.0)
+    A = pt.dirichlet(pt.ChebMat(x, order=2))
+    An = np.asarray(A)
+    npts = (24, n)
+    rng = np.random.default_rng(n)
+    F = rng.standard_normal((2, 24 * n))
+    Fd = torch.from_numpy(F).cuda()
+    plain = pt.AxisSolver(A, npts=npts, axis=1)
+    refined = pt.AxisSolver(A, npts=npts, axis=1, refine=1)
+    y0 = plain.solve(Fd).cpu().numpy()
+    y1 = refined.solve(Fd).cpu().numpy()
+    assert np.array_equal(plain.solve(Fd, refine=1).cpu().numpy(), y1)
+
+    def scaled_residual(y):          # componentwise backward error: |f - A y| / (|A| |y| + |f|)
+        r = oracle.apply_along_axis(An, y, npts, 1) - F
+        return np.max(np.abs(r) / (oracle.abs_bound(An, y, npts, 1) + np.abs(F)))
+
+    r0, r1 = scaled_residual(y0), scaled_residual(y1)
+    assert r1 <= 50 * np.finfo(np.float64).eps, (r0, r1)
+    assert r1 <= r0
+    ref = np.linalg.solve(An, F.reshape(2, n, 24).transpose(1, 0, 2).reshape(n, -1))
+    ref = ref.reshape(n, 2, 24).transpose(1, 0, 2).reshape(2, -1)
+    cond = np.linalg.cond(An)
+    assert np.max(np.abs(y1 - ref)) <= 1e-14 * cond * np.max(np.abs(ref))
+    # host arrays go through the same path
+    assert np.array_equal(refined.solve(F), y1)
