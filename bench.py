@@ -1005,7 +1005,18 @@ def main():
                     help="slab workload: the three derivatives in one read of the field (pt_stencil_grad3_halo)")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="sharded workloads: peer-memory kernels (default) or the NCCL exchange/all_to_all path")
+    ap.add_argument("--deadline", type=float, default=1200.0,
+                    help="seconds after which the process gives up (a stalled rank must not eat the caller's whole budget)")
     args = ap.parse_args()
+    if args.deadline > 0:
+        def give_up():
+            sys.stderr.write(f"bench.py: no result after {args.deadline:.0f} s, giving up\n")
+            sys.stderr.flush()
+            os._exit(3)
+
+        t = threading.Timer(args.deadline, give_up)
+        t.daemon = True
+        t.start()
     spec = workload_spec(args.workload)
     if args.impl == "reference":
         run_reference(args, spec)

@@ -21,7 +21,7 @@
 //     the epilogue (one FMA per element), the middle ROW is a dot product the producers accumulate
 //     from the E (or O) values they form anyway (two independent DFMA chains per thread: a dependent
 //     chain waits for the FP64 pipe behind the DMMAs at every link); the eight partial sums of a column
-//     meet in shared memory and the producer group that stages the tile's last chunk adds and stores them.
+//     travel through shared memory with the tile's last two chunks and the epilogue adds and stores them.
 //     (Accumulating in the consumer warps was measured: the DFMAs stall the DMMA stream, 0.24 vs 0.19 ms.)
 //   * COPY (pencil redistribution): the producers of the first row block also store the field tiles
 //     they load — every element of U passes through their registers exactly once — through a second
@@ -68,13 +68,22 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// Wait for a phase.  A pipeline bug must not hang the GPU (a hung device costs the whole box): the spin
+// is bounded — every failed try_wait has itself waited for the hardware's time limit, so 2^22 of them are
+// far beyond any legitimate wait (tens of microseconds) — and the kernel traps instead, which surfaces as
+// a CUDA error on the host.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   asm volatile(
       "{\n"
-      ".reg .pred p;\n"
+      ".reg .pred p, q;\n"
+      ".reg .u32 spins;\n"
+      "mov.u32 spins, 0;\n"
       "WAIT_LOOP:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra WAIT_DONE;\n"
+      "add.u32 spins, spins, 1;\n"
+      "setp.gt.u32 q, spins, 4194304;\n"
+      "@q trap;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
@@ -373,55 +382,14 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
           *reinterpret_cast<double2*>(Ot + so) = m[r];
         }
       }
-      // the last chunk of a tile that THIS group stages: its partial sums of the middle row go to shared memory
-      const bool mid_last = MIDFIX && mblock == 0 && kc + 2 >= nchunks;
-      if (mid_last) {
+      // the last chunk of a tile that THIS group stages: its partial sums of the middle row ride with it
+      // (visible to the consumers once they have waited for the tile's last two stages)
+      if (MIDFIX && mblock == 0 && kc + 2 >= nchunks) {
         double* buf = midbuf + ((par * 2 + group) * 4 + kr0) * BN + sto;
         *reinterpret_cast<double2*>(buf) = make_double2(__dadd_rn(macc[0][0], macc[1][0]), __dadd_rn(macc[0][1], macc[1][1]));
         macc[0][0] = macc[0][1] = macc[1][0] = macc[1][1] = 0.0;
       }
       mbar_arrive(full + slot);
-      if (mid_last && kc == nchunks - 1) {
-        // ... and the group that stages the tile's LAST chunk finishes the row:
-        //   y[mid] = sum_k D[mid][k] X[k] + D[mid][mid] u[mid]
-        // Its own four warps meet at a named barrier; the other group's partial sums (written before it
-        // arrived on the previous chunk's full barrier) and u[mid] (written with chunk 0) are visible once
-        // that phase has completed.  The producers have the slack for this (the consumers do not:
-        // finishing the row in their epilogue cost 2.3 K cycles of a 43 K-cycle tile).
-        if (group == 0) asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        else asm volatile("bar.sync 2, 128;\n" ::: "memory");
-        if (kr0 == 0 && ok) {
-          mbar_wait(full + (it - 1) % STAGES, ((it - 1) / STAGES) & 1u);
-          const double* mb = midbuf + par * PWARPS * BN + sto;
-          double2 v[PWARPS];
-#pragma unroll
-          for (int w = 0; w < PWARPS; ++w) v[w] = *reinterpret_cast<const double2*>(mb + w * BN);
-          // fixed pairwise order
-          double w0 = __dadd_rn(__dadd_rn(__dadd_rn(v[0].x, v[1].x), __dadd_rn(v[2].x, v[3].x)),
-                                __dadd_rn(__dadd_rn(v[4].x, v[5].x), __dadd_rn(v[6].x, v[7].x)));
-          double w1 = __dadd_rn(__dadd_rn(__dadd_rn(v[0].y, v[1].y), __dadd_rn(v[2].y, v[3].y)),
-                                __dadd_rn(__dadd_rn(v[4].y, v[5].y), __dadd_rn(v[6].y, v[7].y)));
-          const double2 umv = *reinterpret_cast<const double2*>(umid_s + par * BN + sto);
-          const double dmm = rmid_s[nchunks * BK];
-          w0 = __fma_rn(dmm, umv.x, w0);
-          w1 = __fma_rn(dmm, umv.y, w1);
-          int64_t a, b;
-          split_column((tile / p.m_blocks) * BN + sto, p.before, a, b);
-          double s0 = p.alpha, s1 = p.alpha;
-          if (p.scale_mode == PT_SCALE_AFTER) { s0 *= p.scale[a % p.scale_len]; s1 = s0; }
-          else if (p.scale_mode == PT_SCALE_BEFORE) { s0 *= p.scale[b]; s1 *= p.scale[b + 1]; }
-          else if (p.scale_mode == PT_SCALE_ROW) { const double sr = p.scale[p.mid]; s0 *= sr; s1 *= sr; }
-          double o0 = __dmul_rn(s0, w0), o1 = __dmul_rn(s1, w1);
-          const int64_t off = a * p.slab + int64_t(p.mid) * p.before + b;
-          if (p.beta != 0.0) {
-            const double2 c = *reinterpret_cast<const double2*>((SCAT ? p.C : p.Y) + off);
-            o0 = __fma_rn(p.beta, c.x, o0);
-            o1 = __fma_rn(p.beta, c.y, o1);
-          }
-          double* y = SCAT ? map_i_part(p.sc, p.mid) + map_a_part(p.sc, a, b) : p.Y + off;
-          *reinterpret_cast<double2*>(y) = make_double2(o0, o1);
-        }
-      }
       // ---- two chunks further ---------------------------------------------------------------------------
       it += 2;
       advance();
@@ -491,6 +459,33 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
     }
     if (tracing) { tr[1] = clock64(); tr[3] = t_wait; }        // main loop done; cycles spent waiting for data
     if (p.dbg == 3 && acce[0][0][0] != 12345.678) continue;      // timing experiment: no epilogue at all
+    if (MIDFIX && wm == 0 && m_block == 0 && lane < WN * 8) {
+      // y[mid] = sum_k D[mid][k] X[k] + D[mid][mid] u[mid]: the producers left eight partial sums per column
+      // (written before they arrived on the full barriers of the tile's last two chunks, which this warp has
+      // waited for).  Finishing the row in the producer group of the last chunk instead was tried: no faster,
+      // and it needs a wait on the OTHER group's full barrier, whose phase can be lapped — a deadlock hazard.
+      const int par = int((tile / gridDim.x) & 1);
+      const int col = wn * WN * 8 + lane;
+      const int64_t nn = n0 + col;
+      if (nn < p.NN) {
+        const double* mb = midbuf + par * PWARPS * BN + col;
+        // fixed pairwise order (a chain of 7 dependent DADDs is ~2x the latency of the 3-level tree)
+        double v = __dadd_rn(__dadd_rn(__dadd_rn(mb[0], mb[BN]), __dadd_rn(mb[2 * BN], mb[3 * BN])),
+                             __dadd_rn(__dadd_rn(mb[4 * BN], mb[5 * BN]), __dadd_rn(mb[6 * BN], mb[7 * BN])));
+        v = __fma_rn(rmid_s[nchunks * BK], umid_s[par * BN + col], v);
+        int64_t a, b;
+        split_column(nn, p.before, a, b);
+        double sc = p.alpha;
+        if (p.scale_mode == PT_SCALE_AFTER) sc *= p.scale[a % p.scale_len];
+        else if (p.scale_mode == PT_SCALE_BEFORE) sc *= p.scale[b];
+        else if (p.scale_mode == PT_SCALE_ROW) sc *= p.scale[p.mid];
+        double out = __dmul_rn(sc, v);
+        const int64_t off = a * p.slab + int64_t(p.mid) * p.before + b;
+        if (p.beta != 0.0) out = __fma_rn(p.beta, (SCAT ? p.C : p.Y)[off], out);
+        if (SCAT) *(map_i_part(p.sc, p.mid) + map_a_part(p.sc, a, b)) = out;
+        else p.Y[off] = out;
+      }
+    }
     if (tracing) tr[7] = clock64();                              // middle row stored
     eo_epilogue<WR, WN, KCONTIG, true, SCAT, MIDFIX>(p, acce, acco, my_rt, rt0 * 8 + my_rt0 * 8, n0 + wn * WN * 8, g, t,
                                                      cmid_s, umid_s + ((tile / gridDim.x) & 1) * BN + wn * WN * 8);
