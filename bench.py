@@ -506,7 +506,7 @@ def time_steps(ctx, step, steps, warmup):
 # --------------------------------------------------------------------------------------------------
 # device-resident measurement of an un-sharded workload (fields split over ranks, no collective)
 # --------------------------------------------------------------------------------------------------
-def measure_plain(ctx, spec, steps, warmup, e2e=True, sustained_s=0.0):
+def measure_plain(ctx, spec, steps, warmup, e2e=True, sustained_s=0.0, graph=False):
     import torch
 
     import pytristan_b200 as pt
@@ -556,6 +556,25 @@ def measure_plain(ctx, spec, steps, warmup, e2e=True, sustained_s=0.0):
     per_op_ms = [float(np.mean([ev[i][k].elapsed_time(ev[i][k + 1]) for i in range(steps)])) for k in range(nops)]
     mine = {"rank": ctx.rank, "gpu": ctx.local, "ms_per_step": my_ms, "per_op_ms": per_op_ms, **sampler.summary()}
 
+    # ---- launch-bound steps: the same launches captured once per ring slot and replayed as CUDA graphs ----
+    graph_ms = None
+    if graph and all(hasattr(op, "apply") for op in ops):
+        from pytristan_b200.graphs import CapturedApply
+
+        caps = [CapturedApply(ops, ring[k], [ys[0] for ys in outs]) for k in range(ring_len)]
+        for k in range(min(warmup, ring_len)):
+            caps[k].replay()
+        ctx.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(steps, 50)
+        g0.record()
+        for i in range(reps):
+            caps[i % ring_len].replay()
+        g1.record()
+        ctx.barrier()
+        graph_ms = g0.elapsed_time(g1) / reps
+        del caps
+
     # ---- sustained: the same step back to back for >= sustained_s seconds --------------------------------
     sus = None
     if sustained_s > 0:
@@ -604,7 +623,8 @@ def measure_plain(ctx, spec, steps, warmup, e2e=True, sustained_s=0.0):
                  else (0.5 if bool(getattr(op, "even_odd", False)) else 1.0)) for op in ops]
     del ring, outs, ops
     torch.cuda.empty_cache()
-    return dict(ranks=ranks, sustained=sus_ranks, e2e=e2e_ranks, launches=launches, eo_ratio=eo_ratio, nbytes=nbytes)
+    return dict(ranks=ranks, sustained=sus_ranks, e2e=e2e_ranks, launches=launches, eo_ratio=eo_ratio, nbytes=nbytes,
+                graph_ms=graph_ms)
 
 
 def host_link_ceiling(ctx, host_in, host_outs):
@@ -948,7 +968,7 @@ def extra_workloads(ctx, args, threads, recs):
             spec = workload_spec(name)
 
             def one(spec=spec):
-                m = measure_plain(ctx, spec, steps, 3, e2e=False)
+                m = measure_plain(ctx, spec, steps, 3, e2e=False, graph=spec["name"].endswith("_b1"))
                 r0 = m["ranks"][0]
                 ms = r0["ms_per_step"]
                 rec = {"workload": spec["name"], "n_gpus": 1, "scaling": "single GPU", "npts": list(spec["npts"]),
@@ -957,6 +977,11 @@ def extra_workloads(ctx, args, threads, recs):
                        "roofline": roofline_record(spec, r0["per_op_ms"], m["eo_ratio"]),
                        "clocks": {k: r0.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
                        "l2": config_dict(spec)["l2"], "gpu_launches": steps * m["launches"]}
+                if m["graph_ms"] is not None:
+                    # the eager step is bound by the host (~25 us of Python + ctypes per launch): same kernels,
+                    # captured once per input buffer and replayed (pytristan_b200.graphs.CapturedApply)
+                    rec["cuda_graph"] = {"ms_per_step": m["graph_ms"], "value": spec["points_per_step"] / (m["graph_ms"] * 1e-3),
+                                         "unit": "points/s", "api": "pytristan_b200.graphs.CapturedApply(ops, u, outs).replay()"}
                 if not args.no_cpu:
                     rec["cpu_baseline"] = cpu_baseline_record(spec, threads, steps=2, warmup=1)
                 return rec

@@ -12,6 +12,7 @@ from .operators import __all__ as _op_all
 from .host import apply_host, launches_per_apply  # noqa: F401
 from .fused import gradient  # noqa: F401
 from .solve import AxisSolver, dirichlet, with_rows  # noqa: F401
+from .graphs import CapturedApply  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = list(_grid_all) + list(_op_all) + ["apply_host", "launches_per_apply", "gradient", "AxisSolver", "dirichlet", "with_rows", "__version__"]
+__all__ = list(_grid_all) + list(_op_all) + ["apply_host", "launches_per_apply", "gradient", "AxisSolver", "dirichlet", "with_rows", "CapturedApply", "__version__"]

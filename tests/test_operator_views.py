@@ -147,3 +147,35 @@ def test_first_apply_neither_allocates_symmetry_scratch_nor_changes_the_choice()
     x = np.linspace(0.0, 1.0, 50) ** 2            # one-sided stretching: not symmetric
     B = pt.ChebMat(x, order=1)
     assert B._eo is False and not B.even_odd
+
+
+def test_captured_apply_replays_the_same_bits():
+    """CUDA-graph replay of operator applications (launch-bound regime): same kernels, same bits, and the
+    graph follows in-place refills of its input buffer."""
+    import torch
+
+    import pytristan_b200 as pt
+
+    clear_grids()
+    try:
+        g = pt.get_polar_grid(64, 24, axes=[1], mappers=[pt.cheb], fornberg=True)
+        lap = pt.PolarLaplacian(g)
+        x = pt.cheb(65, -1.0, 1.0)
+        D = pt.ChebMat(x, order=1)
+        D.npts, D.axis = (32, 65), 1
+        F = pt.FinDiffMat(np.linspace(0.0, 1.0, 32), order=1, accuracy=4)
+        F.npts, F.axis = (32, 65), 0
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        for ops, size in (([lap], 3 * 64 * 48), ([D, F], 5 * 32 * 65)):
+            u = torch.randn(size, dtype=torch.float64, device="cuda", generator=gen)
+            cap = pt.CapturedApply(ops, u)
+            for _ in range(3):
+                u.copy_(torch.randn(size, dtype=torch.float64, device="cuda", generator=gen))
+                outs = cap.replay()
+                torch.cuda.synchronize()
+                for op, y in zip(ops, outs):
+                    assert torch.equal(y, op.apply(u).reshape(-1))
+        with pytest.raises(TypeError):
+            pt.CapturedApply([D], np.zeros(32 * 65))
+    finally:
+        clear_grids()
