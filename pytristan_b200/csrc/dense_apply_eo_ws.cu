@@ -227,16 +227,22 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
                             : 2 * (ptid & 31);                // K1: column pair of the tile
     const int64_t pass_step = KCONTIG ? int64_t(16) * n : 4 * p.before;
     const int64_t chunk_step = KCONTIG ? int64_t(BK) : int64_t(BK) * p.before;
-    const int64_t my_tiles = (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    const int64_t total_it = my_tiles * nchunks;
+    // tile indices fit 32 bits (checked on the host): no 64-bit divisions in the loops
+    const unsigned ntiles = unsigned(p.total_tiles), mblocks = unsigned(p.m_blocks);
+    const unsigned my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t total_it = int64_t(my_tiles) * nchunks;
 
     // ---- position in the (tile, chunk) sequence + this thread's forward / mirrored source pointers ----
-    int64_t tile = blockIdx.x;
+    unsigned tile = blockIdx.x, ti = 0;      // tile index; count of this CTA's tiles so far
+    int mblock = 0;                          // row block of the tile
+    int64_t n0 = 0;                          // first column of the tile
     int kc = 0;
     const double *fwd = p.U, *mir = p.U;
     unsigned ok = 0;          // K2: validity of the column of each pass; K1: all-or-nothing
     auto setup = [&]() {
-      const int64_t n0 = (tile / p.m_blocks) * BN;
+      const unsigned nb = tile / mblocks;
+      mblock = int(tile - nb * mblocks);
+      n0 = int64_t(nb) * BN;
       ok = 0;
       kc = 0;
       if (KCONTIG) {
@@ -263,7 +269,8 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
       mir -= chunk_step;
       if (++kc == nchunks) {
         tile += gridDim.x;
-        if (tile < p.total_tiles) setup();
+        ++ti;
+        if (tile < ntiles) setup();
         else ok = 0;
       }
     };
@@ -296,12 +303,10 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
       // ---- chunk `it` = (tile, kc): registers -> E / O tiles of ring slot it % STAGES ----------------
       const int slot = it % STAGES;
       const unsigned round = it / STAGES;
-      const int mblock = int(tile % p.m_blocks);
-      const int par = int((tile / gridDim.x) & 1);
+      const int par = int(ti & 1);
       if (p.trace && ptid == 0) {
         const long long t0 = clock64();
         if (round > 0) mbar_wait(empty + slot, (round - 1) & 1u);
-        const int64_t ti = tile / gridDim.x;
         if (ti < 16) {
           long long* tr = p.trace + (int64_t(blockIdx.x) * 16 + ti) * 8;
           tr[4] += clock64() - t0;                 // cycles the producers waited for a free slot
@@ -322,7 +327,6 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
       if (COPY && mblock == 0) {
         // the field itself, redistributed: forward pieces cover rows i < H, mirrored pieces rows i >= n - H
         const int k0 = kc * BK;
-        const int64_t n0 = (tile / p.m_blocks) * BN;
         if (KCONTIG) {
           const int kf = k0 + c2, km = n - 2 - kf;           // s_i == 1 on the contiguous axis
           double* df = map_i_part(p.cp, kf);
@@ -415,11 +419,14 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
   // epilogue together and leave the DMMA pipe idle for its whole duration.  The second row half starts two
   // chunks late (it waits for chunk 2 to land before it touches chunk 0); the offset then sustains itself:
   // while one warp stores, the other has the pipe to itself.  tuning hook: pt_debug_set_eo_ws(6) = no stagger
-  if (wm == 1 && p.dbg != 6 && nchunks * ((p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) > STAGGER)
+  const unsigned ntiles = unsigned(p.total_tiles), mblocks = unsigned(p.m_blocks);
+  if (wm == 1 && p.dbg != 6 && int64_t(nchunks) * ((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) > STAGGER)
     mbar_wait(full + STAGGER, 0);
-  for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    const int m_block = int(tile % p.m_blocks);
-    const int64_t n0 = (tile / p.m_blocks) * BN;
+  unsigned ti = 0;                             // count of this CTA's tiles so far
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+    const unsigned nb = tile / mblocks;
+    const int m_block = int(tile - nb * mblocks);
+    const int64_t n0 = int64_t(nb) * BN;
     const int rt0 = m_block * (BMH / 8);
     const int rt_count = min(BMH / 8, rtiles_total - rt0);
     const int q = (rt_count + CW_M - 1) / CW_M;
@@ -433,8 +440,8 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
 #pragma unroll
       for (int j = 0; j < WN; ++j) { acce[i][j][0] = acce[i][j][1] = 0.0; acco[i][j][0] = acco[i][j][1] = 0.0; }
 
-    const bool tracing = p.trace && tid == 0 && (tile / gridDim.x) < 16;
-    long long* tr = tracing ? p.trace + (int64_t(blockIdx.x) * 16 + tile / gridDim.x) * 8 : nullptr;
+    const bool tracing = p.trace && tid == 0 && ti < 16;
+    long long* tr = tracing ? p.trace + (int64_t(blockIdx.x) * 16 + ti) * 8 : nullptr;
     long long t_wait = 0;
     if (tracing) tr[0] = clock64();                 // consumer starts the tile
     for (int kc = 0; kc < nchunks; ++kc, ++it) {
@@ -464,7 +471,7 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
       // (written before they arrived on the full barriers of the tile's last two chunks, which this warp has
       // waited for).  Finishing the row in the producer group of the last chunk instead was tried: no faster,
       // and it needs a wait on the OTHER group's full barrier, whose phase can be lapped — a deadlock hazard.
-      const int par = int((tile / gridDim.x) & 1);
+      const int par = int(ti & 1);
       const int col = wn * WN * 8 + lane;
       const int64_t nn = n0 + col;
       if (nn < p.NN) {
@@ -488,7 +495,7 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
     }
     if (tracing) tr[7] = clock64();                              // middle row stored
     eo_epilogue<WR, WN, KCONTIG, true, SCAT, MIDFIX>(p, acce, acco, my_rt, rt0 * 8 + my_rt0 * 8, n0 + wn * WN * 8, g, t,
-                                                     cmid_s, umid_s + ((tile / gridDim.x) & 1) * BN + wn * WN * 8);
+                                                     cmid_s, umid_s + (ti & 1) * BN + wn * WN * 8);
     if (tracing) tr[2] = clock64();                              // epilogue done
   }
 }
@@ -593,6 +600,7 @@ bool ws_eligible(int n, const double* U, const double* Y, const double* C, int64
   const int64_t NN = after * before;
   const int64_t tiles = int64_t(s.m_blocks) * ((NN + BN - 1) / BN);
   if (tiles < pt::sm_count()) return false;            // small fields: the small-tile cp.async kernel fills the GPU better
+  if (tiles >= (int64_t(1) << 31)) return false;       // the kernel indexes tiles with 32 bits
   if (!aligned16(U)) return false;
   if (copy_map) {      // 16-byte stores of the field pieces: even strides, pieces never straddle two destinations
     if ((copy_map->s_outer | copy_map->s_inner | copy_map->offset | copy_map->chunk) & 1) return false;
