@@ -26,7 +26,7 @@ namespace {
 struct FftParams {
   const double* __restrict__ U;
   double* __restrict__ Y;
-  const double2* __restrict__ tw;   // tw[m] = exp(-2 pi i m / n), m < n
+  const double2* __restrict__ tw;   // tw[n - L + i] = exp(-2 pi i * i / L), i < 3L/4, for L = n, n/4, n/16, ...
   int64_t after, before;
   int64_t ngroups, groups_per_a;
   int order;
@@ -58,36 +58,58 @@ __device__ __forceinline__ void dft4(double2& x0, double2& x1, double2& x2, doub
   x3 = csub(d02, r);
 }
 
+// Twiddle table: one run of 3L/4 roots of unity per radix-4 level L = N, N/4, N/16, ... (run L starts
+// at N - L; N complex numbers in all), so that the lanes of a warp, which run along j, read
+// consecutive entries at every level.  TWS: the table has been copied to shared memory.
+// MODE bit 0: table in shared memory; bit 1: W^2j and W^3j derived from W^j (one load per level)
+template <int TWS>
+__device__ __forceinline__ double2 twiddle(const double2* __restrict__ tw, int idx) {
+  return (TWS & 1) ? tw[idx] : __ldg(tw + idx);
+}
+template <int TWS>
+__device__ __forceinline__ void twiddles3(const double2* __restrict__ t, int j, double2& w1, double2& w2, double2& w3) {
+  w1 = twiddle<TWS>(t, j);
+  if (TWS & 2) {
+    w2 = make_double2(fma(w1.x, w1.x, -w1.y * w1.y), 2.0 * w1.x * w1.y);
+    w3 = cmul(w1, w2);
+  } else {
+    w2 = twiddle<TWS>(t, 2 * j);
+    w3 = twiddle<TWS>(t, 3 * j);
+  }
+}
+
 // One radix-4 level on a block of length L at offset j inside its quarter.
 // forward: DFT over the 4 elements, then twiddle w_L^(j p); inverse: conj twiddle, then inverse DFT.
-template <int N, int L, bool INV>
+template <int N, int L, bool INV, int TWS>
 __device__ __forceinline__ void level4(double2& v0, double2& v1, double2& v2, double2& v3, int j,
                                        const double2* __restrict__ tw) {
-  const int m = j * (N / L);
+  const double2* __restrict__ t = tw + (N - L);
+  double2 w1, w2, w3;
+  if (L > 4) twiddles3<TWS>(t, j, w1, w2, w3);
   if (INV) {
-    if (L > 4) { v1 = cmulc(v1, __ldg(tw + m)); v2 = cmulc(v2, __ldg(tw + 2 * m)); v3 = cmulc(v3, __ldg(tw + 3 * m)); }
+    if (L > 4) { v1 = cmulc(v1, w1); v2 = cmulc(v2, w2); v3 = cmulc(v3, w3); }
     dft4<true>(v0, v1, v2, v3);
   } else {
     dft4<false>(v0, v1, v2, v3);
-    if (L > 4) { v1 = cmul(v1, __ldg(tw + m)); v2 = cmul(v2, __ldg(tw + 2 * m)); v3 = cmul(v3, __ldg(tw + 3 * m)); }
+    if (L > 4) { v1 = cmul(v1, w1); v2 = cmul(v2, w2); v3 = cmul(v3, w3); }
   }
 }
 
 // Radix-16 butterfly = the radix-4 levels of block lengths L and L/4 on the 16 elements
 // v[a][b] = x[base + a*(L/4) + b*(L/16)], base = blk*L + j, j < L/16.
-template <int N, int L, bool INV>
+template <int N, int L, bool INV, int TWS>
 __device__ __forceinline__ void core16(double2 (&v)[4][4], int j, const double2* __restrict__ tw) {
   constexpr int Q2 = L / 16;
   if (!INV) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) level4<N, L, false>(v[0][b], v[1][b], v[2][b], v[3][b], j + b * Q2, tw);
+    for (int b = 0; b < 4; ++b) level4<N, L, false, TWS>(v[0][b], v[1][b], v[2][b], v[3][b], j + b * Q2, tw);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) level4<N, L / 4, false>(v[a][0], v[a][1], v[a][2], v[a][3], j, tw);
+    for (int a = 0; a < 4; ++a) level4<N, L / 4, false, TWS>(v[a][0], v[a][1], v[a][2], v[a][3], j, tw);
   } else {
 #pragma unroll
-    for (int a = 0; a < 4; ++a) level4<N, L / 4, true>(v[a][0], v[a][1], v[a][2], v[a][3], j, tw);
+    for (int a = 0; a < 4; ++a) level4<N, L / 4, true, TWS>(v[a][0], v[a][1], v[a][2], v[a][3], j, tw);
 #pragma unroll
-    for (int b = 0; b < 4; ++b) level4<N, L, true>(v[0][b], v[1][b], v[2][b], v[3][b], j + b * Q2, tw);
+    for (int b = 0; b < 4; ++b) level4<N, L, true, TWS>(v[0][b], v[1][b], v[2][b], v[3][b], j + b * Q2, tw);
   }
 }
 
@@ -178,12 +200,12 @@ __device__ __forceinline__ void split_item(int item, int& sq, int& t) {
 
 // One radix-16 stage on blocks of length L.  GIN: elements come from global memory (first forward
 // stage); GOUT: results go to global memory (last inverse stage); otherwise the shared tile.
-template <int LOG2N, int L, bool INV, bool GIN, bool GOUT, bool STRIDED, int NT, int TILE>
+template <int LOG2N, int L, bool INV, bool GIN, bool GOUT, bool STRIDED, int NT, int TILE, int TWS>
 __device__ __forceinline__ void stage16(double2* data, const double2* __restrict__ tw,
-                                        const GlobalIO<LOG2N, STRIDED>& io) {
+                                        const GlobalIO<LOG2N, STRIDED>& io, int tid) {
   using P = FftPlan<LOG2N, TILE>;
   constexpr int N = P::N, Q1 = L / 4, Q2 = L / 16, PER_SEQ = N / 16;
-  for (int item = threadIdx.x; item < P::S * PER_SEQ; item += NT) {
+  for (int item = tid; item < P::S * PER_SEQ; item += NT) {
     int sq, t;
     split_item<P::S, PER_SEQ, STRIDED>(item, sq, t);
     // lanes run along j when a sixteenth of the block spans a quarter-warp, otherwise along the
@@ -200,7 +222,7 @@ __device__ __forceinline__ void stage16(double2* data, const double2* __restrict
         const int i = base + a * Q1 + b * Q2;
         v[a][b] = GIN ? io.load(sq, i) : x[padi(i)];
       }
-    core16<N, L, INV>(v, j, tw);
+    core16<N, L, INV, TWS>(v, j, tw);
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -228,13 +250,13 @@ __device__ __forceinline__ double2 apply_symbol(double2 z, int k, int n, const F
 }
 
 // Middle stage on blocks of length LT: last forward levels, symbol, first inverse levels.
-template <int LOG2N, bool GLOBAL, bool STRIDED, int NT, int TILE>
+template <int LOG2N, bool GLOBAL, bool STRIDED, int NT, int TILE, int TWS>
 __device__ __forceinline__ void stage_middle(double2* data, const double2* __restrict__ tw,
-                                             const GlobalIO<LOG2N, STRIDED>& io, const FftParams& p) {
+                                             const GlobalIO<LOG2N, STRIDED>& io, const FftParams& p, int tid) {
   using P = FftPlan<LOG2N, TILE>;
   constexpr int N = P::N, LT = P::LT, PER_SEQ = N / LT;
   constexpr int BLK_DIGITS = (LOG2N - P::LT_LOG) / 2;   // base-4 digits of the block index
-  for (int item = threadIdx.x; item < P::S * PER_SEQ; item += NT) {
+  for (int item = tid; item < P::S * PER_SEQ; item += NT) {
     int sq, blk;
     split_item<P::S, PER_SEQ, STRIDED>(item, sq, blk);
     double2* x = data + sq * P::PITCH;
@@ -246,12 +268,12 @@ __device__ __forceinline__ void stage_middle(double2* data, const double2* __res
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) w[a][b] = GLOBAL ? io.load(sq, base + 4 * a + b) : x[padi(base + 4 * a + b)];
-      core16<N, 16, false>(w, 0, tw);
+      core16<N, 16, false, TWS>(w, 0, tw);
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) w[a][b] = apply_symbol(w[a][b], k0 + (N / 16) * (a + 4 * b), N, p);
-      core16<N, 16, true>(w, 0, tw);
+      core16<N, 16, true, TWS>(w, 0, tw);
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -265,8 +287,8 @@ __device__ __forceinline__ void stage_middle(double2* data, const double2* __res
       for (int q = 0; q < LT; ++q) v[q] = GLOBAL ? io.load(sq, base + q) : x[padi(base + q)];
       if constexpr (LT == 8) {
         // radix-4 level on L = 8 (quarter 2: j = 0, 1), then radix-2 on the pairs
-        level4<N, 8, false>(v[0], v[2], v[4], v[6], 0, tw);
-        level4<N, 8, false>(v[1], v[3], v[5], v[7], 1, tw);
+        level4<N, 8, false, TWS>(v[0], v[2], v[4], v[6], 0, tw);
+        level4<N, 8, false, TWS>(v[1], v[3], v[5], v[7], 1, tw);
 #pragma unroll
         for (int a = 0; a < 4; ++a) level2(v[2 * a], v[2 * a + 1]);
 #pragma unroll
@@ -275,13 +297,13 @@ __device__ __forceinline__ void stage_middle(double2* data, const double2* __res
           for (int e = 0; e < 2; ++e) v[2 * a + e] = apply_symbol(v[2 * a + e], k0 + (N / 8) * (a + 4 * e), N, p);
 #pragma unroll
         for (int a = 0; a < 4; ++a) level2(v[2 * a], v[2 * a + 1]);
-        level4<N, 8, true>(v[0], v[2], v[4], v[6], 0, tw);
-        level4<N, 8, true>(v[1], v[3], v[5], v[7], 1, tw);
+        level4<N, 8, true, TWS>(v[0], v[2], v[4], v[6], 0, tw);
+        level4<N, 8, true, TWS>(v[1], v[3], v[5], v[7], 1, tw);
       } else if constexpr (LT == 4) {
-        level4<N, 4, false>(v[0], v[1], v[2], v[3], 0, tw);
+        level4<N, 4, false, TWS>(v[0], v[1], v[2], v[3], 0, tw);
 #pragma unroll
         for (int q = 0; q < 4; ++q) v[q] = apply_symbol(v[q], k0 + (N / 4) * q, N, p);
-        level4<N, 4, true>(v[0], v[1], v[2], v[3], 0, tw);
+        level4<N, 4, true, TWS>(v[0], v[1], v[2], v[3], 0, tw);
       } else {
         level2(v[0], v[1]);
 #pragma unroll
@@ -297,13 +319,23 @@ __device__ __forceinline__ void stage_middle(double2* data, const double2* __res
   }
 }
 
-template <int LOG2N, bool STRIDED, int NT, int TILE>
-__global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) fourier_fft_kernel(const FftParams p) {
+template <int NT, int TWS>
+constexpr int fft_min_ctas() { return NT == 128 ? ((TWS & 1) ? 4 : 5) : 2; }
+
+template <int LOG2N, bool STRIDED, int NT, int TILE, int TWS>
+__global__ void __launch_bounds__(NT, fft_min_ctas<NT, TWS>()) fourier_fft_kernel(const FftParams p) {
   using P = FftPlan<LOG2N, TILE>;
   constexpr int N = P::N;
   extern __shared__ __align__(16) double2 fsm[];
+  const int tid = threadIdx.x;
   double2* data = fsm;
   const double2* __restrict__ tw = p.tw;
+  if (TWS & 1) {
+    double2* tws = fsm + P::S * P::PITCH;
+    for (int i = threadIdx.x; i < N; i += NT) tws[i] = __ldg(p.tw + i);
+    __syncthreads();
+    tw = tws;
+  }
   const int64_t hb = p.before >> 1;
 
   for (int64_t g = blockIdx.x; g < p.ngroups; g += gridDim.x) {
@@ -320,48 +352,313 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) fourier_fft_kernel(cons
       if (p.scale) io.slab_scale = p.scale[a % p.scale_len];
     }
     if constexpr (P::NR16 == 0) {
-      stage_middle<LOG2N, true, STRIDED, NT, TILE>(data, tw, io, p);
+      stage_middle<LOG2N, true, STRIDED, NT, TILE, TWS>(data, tw, io, p, tid);
     } else {
       constexpr int L2 = N >= 256 ? N / 16 : 16;   // block length of the second radix-16 stage
       __syncthreads();   // the previous group's last stage has read the tile
-      stage16<LOG2N, N, false, true, false, STRIDED, NT, TILE>(data, tw, io);
+      stage16<LOG2N, N, false, true, false, STRIDED, NT, TILE, TWS>(data, tw, io, tid);
       __syncthreads();
       if constexpr (P::NR16 == 2) {
-        stage16<LOG2N, L2, false, false, false, STRIDED, NT, TILE>(data, tw, io);
+        stage16<LOG2N, L2, false, false, false, STRIDED, NT, TILE, TWS>(data, tw, io, tid);
         __syncthreads();
       }
-      stage_middle<LOG2N, false, STRIDED, NT, TILE>(data, tw, io, p);
+      stage_middle<LOG2N, false, STRIDED, NT, TILE, TWS>(data, tw, io, p, tid);
       __syncthreads();
       if constexpr (P::NR16 == 2) {
-        stage16<LOG2N, L2, true, false, false, STRIDED, NT, TILE>(data, tw, io);
+        stage16<LOG2N, L2, true, false, false, STRIDED, NT, TILE, TWS>(data, tw, io, tid);
         __syncthreads();
       }
-      stage16<LOG2N, N, true, false, true, STRIDED, NT, TILE>(data, tw, io);
+      stage16<LOG2N, N, true, false, true, STRIDED, NT, TILE, TWS>(data, tw, io, tid);
     }
   }
 }
 
+// entry idx of the table: run L covers [n - L, n - L/4)
+
+// ---- n = 1024 on the contiguous axis: one warp per complex sequence, 1024 = 32 x 32 -------------
+// Lane j holds x[j + 32 q], q < 32, in registers and takes it through the radix-4, radix-4, radix-2
+// levels of block lengths 1024, 256, 64 (table twiddles); one trip through the warp's shared tile
+// regroups the sequence into 32 blocks of 32 consecutive elements, one per lane, which go through the
+// levels 32, 8, 2 (twiddles are compile-time constants), the symbol, and back; a second trip returns
+// the stride-32 layout for the inverse levels 64, 256, 1024 and the stores.  Two shared round trips
+// instead of four, no CTA barrier (warps are independent and drift apart in phase, which is what
+// overlaps the loads of one with the butterflies of the others), a third of the twiddle loads.
+// The price is 32 complex numbers per thread: 168 registers, 12 warps per SM.
+
+__device__ __forceinline__ double cos32(int m) {   // cos(2 pi m / 32); m is a compile-time constant after unrolling
+  m &= 31;
+  const int k = m <= 8 ? m : (m <= 16 ? 16 - m : (m <= 24 ? m - 16 : 32 - m));
+  double q = 0.0;
+  switch (k) {
+    case 0: q = 1.0; break;
+    case 1: q = 0.98078528040323043; break;
+    case 2: q = 0.92387953251128674; break;
+    case 3: q = 0.83146961230254524; break;
+    case 4: q = 0.70710678118654757; break;
+    case 5: q = 0.55557023301960218; break;
+    case 6: q = 0.38268343236508978; break;
+    case 7: q = 0.19509032201612828; break;
+    default: q = 0.0;
+  }
+  return (m <= 8 || m >= 24) ? q : -q;
+}
+
+// a * W_32^m (forward) or a * conj(W_32^m) (inverse)
+template <bool INV>
+__device__ __forceinline__ double2 rot32(double2 a, int m) {
+  m &= 31;
+  if (m == 0) return a;
+  if (m == 8) return INV ? mul_pi(a) : mul_mi(a);
+  if (m == 16) return make_double2(-a.x, -a.y);
+  if (m == 24) return INV ? mul_mi(a) : mul_pi(a);
+  const double2 w = make_double2(cos32(m), -cos32(m - 8));
+  return INV ? cmulc(a, w) : cmul(a, w);
+}
+
+// radix-4 level with constant twiddles W_32^(step * p)
+template <bool INV>
+__device__ __forceinline__ void level4c(double2& v0, double2& v1, double2& v2, double2& v3, int step) {
+  if (INV) {
+    v1 = rot32<true>(v1, step); v2 = rot32<true>(v2, 2 * step); v3 = rot32<true>(v3, 3 * step);
+    dft4<true>(v0, v1, v2, v3);
+  } else {
+    dft4<false>(v0, v1, v2, v3);
+    v1 = rot32<false>(v1, step); v2 = rot32<false>(v2, 2 * step); v3 = rot32<false>(v3, 3 * step);
+  }
+}
+
+// z * alpha/n * (i ks)^order; ORDER = 0: any order (p.order), else the compile-time order
+template <int ORDER>
+__device__ __forceinline__ double2 symbol_ks(double2 z, double ks, const FftParams& p) {
+  double pw = p.alpha_over_n;
+  if (ORDER == 1) pw *= ks;
+  else if (ORDER == 2) pw *= ks * ks;
+  else {
+#pragma unroll 1
+    for (int o = 0; o < p.order; ++o) pw *= ks;
+  }
+  switch ((ORDER ? ORDER : p.order) & 3) {
+    case 0: return make_double2(z.x * pw, z.y * pw);
+    case 1: return make_double2(-z.y * pw, z.x * pw);
+    case 2: return make_double2(-z.x * pw, -z.y * pw);
+    default: return make_double2(z.y * pw, -z.x * pw);
+  }
+}
+
+__device__ __forceinline__ unsigned smem_addr(const void* ptr) { return unsigned(__cvta_generic_to_shared(ptr)); }
+// bounded wait (a pipeline bug must trap, not hang the GPU)
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p, q;\n.reg .u32 spins;\nmov.u32 spins, 0;\n"
+      "FFT_WAIT: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra FFT_DONE;\n"
+      "add.u32 spins, spins, 1;\nsetp.gt.u32 q, spins, 4194304;\n@q trap;\nbra FFT_WAIT;\nFFT_DONE:\n}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+constexpr int W1K_WARPS = 1;                 // warps per CTA (warps are independent: no reason to tie them together)
+constexpr int W1K_PITCH = 33 * 32;           // complex slots per warp tile: i + i/32
+constexpr size_t W1K_SMEM = size_t(W1K_WARPS) * W1K_PITCH * sizeof(double2) + 16;   // + the warp's mbarrier
+
+template <int MODE, int ORDER, int CTAS, bool PF>
+__global__ void __launch_bounds__(W1K_WARPS * 32, CTAS) fourier_fft1024_warp_kernel(const FftParams p) {
+  constexpr int N = 1024;
+  extern __shared__ __align__(16) double2 fsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double2* x = fsm + warp * W1K_PITCH;
+  const double2* __restrict__ tw = p.tw;
+  const int64_t nseq = (p.after + 1) >> 1;
+  // low frequency digits of the block a lane owns in the middle stage: lane = 8 d1 + 2 d2 + d3
+  const int klow = (lane >> 3) + 4 * ((lane >> 1) & 3) + 16 * (lane & 1);
+  const double ks_low = double(klow) * p.s;
+  const bool drop_nyquist = klow == 0 && (p.order & 1);      // odd orders: the mode n/2 is dropped
+  // PF: the row pair of the warp's NEXT sequence is copied into the tile by the bulk-copy engine as soon as
+  // the last stage has read the tile, i.e. under that stage's butterflies and stores; the first stage
+  // then reads its inputs from shared memory instead of waiting on HBM.
+  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + W1K_WARPS * W1K_PITCH) + warp;
+  const double* raw = reinterpret_cast<const double*>(x);
+  auto fetch = [&](int64_t sq) {              // lane 0 only
+    const unsigned bytes = (2 * sq + 1 < p.after) ? 2 * N * 8 : N * 8;
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_addr(x)), "l"(p.U + 2 * sq * N), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+  };
+  unsigned phase = 0;
+  if (PF) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(1));
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      const int64_t first = int64_t(blockIdx.x) * W1K_WARPS + warp;
+      if (first < nseq) fetch(first);
+    }
+    __syncwarp();
+  }
+
+  for (int64_t seq = int64_t(blockIdx.x) * W1K_WARPS + warp; seq < nseq; seq += int64_t(gridDim.x) * W1K_WARPS) {
+    const int64_t r0 = 2 * seq;
+    const bool two = r0 + 1 < p.after;
+    // Everything that depends on the lane only (twiddles, frequencies) is loop invariant, and hoisting it
+    // out of the loop costs ~150 registers that are then spilled: make it look loop variant instead.
+    int ln = lane;
+    double ksl = ks_low;
+    asm volatile("" : "+r"(ln), "+d"(ksl));
+    const double* __restrict__ u0 = p.U + r0 * N + lane;
+    const double* __restrict__ u1 = u0 + (two ? N : 0);
+    double2 v[32];
+    if (PF) {
+      mbar_wait_parity(bar, phase);
+      phase ^= 1;
+      const double* r1 = raw + (two ? N : 0);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) { v[q].x = raw[lane + 32 * q]; v[q].y = r1[lane + 32 * q]; }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 32; ++q) { v[q].x = u0[32 * q]; v[q].y = u1[32 * q]; }
+    }
+    if (!two) {
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q].y = 0.0;
+    }
+    // forward levels 1024, 256 (radix 4) and 64 (radix 2) on the elements lane + 32 q
+#pragma unroll
+    for (int r = 0; r < 8; ++r) level4<N, 1024, false, MODE>(v[r], v[8 + r], v[16 + r], v[24 + r], ln + 32 * r, tw);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+        level4<N, 256, false, MODE>(v[8 * a + r], v[8 * a + 2 + r], v[8 * a + 4 + r], v[8 * a + 6 + r], ln + 32 * r, tw);
+    double2 w64 = twiddle<MODE>(tw + (N - 64), ln);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const double2 sm = cadd(v[2 * m], v[2 * m + 1]), df = csub(v[2 * m], v[2 * m + 1]);
+      v[2 * m] = sm; v[2 * m + 1] = cmul(df, w64);
+    }
+    __syncwarp();                            // the previous sequence's last reads of the tile are done
+#pragma unroll
+    for (int q = 0; q < 32; ++q) x[lane + 33 * q] = v[q];
+    __syncwarp();
+    // middle: block `lane`, elements 32 lane + r
+#pragma unroll
+    for (int r = 0; r < 32; ++r) v[r] = x[33 * lane + r];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) level4c<false>(v[j], v[8 + j], v[16 + j], v[24 + j], j);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) level4c<false>(v[8 * a + j], v[8 * a + 2 + j], v[8 * a + 4 + j], v[8 * a + 6 + j], 4 * j);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) level2(v[2 * m], v[2 * m + 1]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          // frequency klow + 32 (a + 4 b + 16 c), taken in (-n/2, n/2]
+          double ks = fma(double(32 * (a + 4 * b) - 512 * c), p.s, ksl);
+          if (a == 0 && b == 0 && c == 1 && drop_nyquist) ks = 0.0;
+          v[8 * a + 2 * b + c] = symbol_ks<ORDER>(v[8 * a + 2 * b + c], ks, p);
+        }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) level2(v[2 * m], v[2 * m + 1]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) level4c<true>(v[8 * a + j], v[8 * a + 2 + j], v[8 * a + 4 + j], v[8 * a + 6 + j], 4 * j);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) level4c<true>(v[j], v[8 + j], v[16 + j], v[24 + j], j);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) x[33 * lane + r] = v[r];
+    __syncwarp();
+    // inverse levels 64, 256, 1024 on the elements lane + 32 q
+#pragma unroll
+    for (int q = 0; q < 32; ++q) v[q] = x[lane + 33 * q];
+    if (PF) {
+      __syncwarp();                          // every lane has its elements: the tile is free for the next row pair
+      const int64_t nxt = seq + int64_t(gridDim.x) * W1K_WARPS;
+      if (lane == 0 && nxt < nseq) fetch(nxt);
+    }
+    w64 = twiddle<MODE>(tw + (N - 64), ln);   // reloaded: cheaper than 4 registers held across the middle stage
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const double2 t = cmulc(v[2 * m + 1], w64);
+      v[2 * m + 1] = csub(v[2 * m], t); v[2 * m] = cadd(v[2 * m], t);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+        level4<N, 256, true, MODE>(v[8 * a + r], v[8 * a + 2 + r], v[8 * a + 4 + r], v[8 * a + 6 + r], ln + 32 * r, tw);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) level4<N, 1024, true, MODE>(v[r], v[8 + r], v[16 + r], v[24 + r], ln + 32 * r, tw);
+    // stores: row r0 takes the real parts, row r0 + 1 the imaginary parts
+    double s0 = 1.0, s1 = 1.0;
+    if (p.scale) { s0 = p.scale[r0 % p.scale_len]; s1 = p.scale[(r0 + 1) % p.scale_len]; }
+    double* __restrict__ y0 = p.Y + r0 * N + lane;
+    double* __restrict__ y1 = y0 + N;
+    const double beta = p.beta;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      double a0 = v[q].x, a1 = v[q].y;
+      if (p.scale) { a0 *= s0; a1 *= s1; }
+      if (beta != 0.0) { a0 = fma(beta, y0[32 * q], a0); if (two) a1 = fma(beta, y1[32 * q], a1); }
+      y0[32 * q] = a0;
+      if (two) y1[32 * q] = a1;
+    }
+  }
+}
+
+template <int MODE, int ORDER, int CTAS, bool PF>
+int launch_fft1024_warp_o(FftParams& p, cudaStream_t st) {
+  auto kern = fourier_fft1024_warp_kernel<MODE, ORDER, CTAS, PF>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  PT_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(W1K_SMEM)));
+    attr_set[dev] = true;
+  }
+  const int64_t nseq = (p.after + 1) / 2;
+  int64_t grid = int64_t(pt::sm_count()) * CTAS;
+  const int64_t need = (nseq + W1K_WARPS - 1) / W1K_WARPS;
+  if (grid > need) grid = need;
+  kern<<<unsigned(grid), W1K_WARPS * 32, W1K_SMEM, st>>>(p);
+  return pt::check_launch("pt_fourier_apply");
+}
+
+template <int MODE, int CTAS, bool PF>
+int launch_fft1024_warp(FftParams& p, cudaStream_t st) {
+  if (p.order == 1) return launch_fft1024_warp_o<MODE, 1, CTAS, PF>(p, st);
+  if (p.order == 2) return launch_fft1024_warp_o<MODE, 2, CTAS, PF>(p, st);
+  return launch_fft1024_warp_o<MODE, 0, CTAS, PF>(p, st);
+}
+
 __global__ void twiddle_kernel(double2* tw, int n) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= n) return;
-  double sn, cs;
-  sincospi(2.0 * double(m) / double(n), &sn, &cs);
-  tw[m] = make_double2(cs, -sn);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  int L = n;
+  while (L >= 4 && idx >= n - L / 4) L >>= 2;
+  double sn = 0.0, cs = 1.0;
+  if (L >= 4) sincospi(2.0 * double(idx - (n - L)) / double(L), &sn, &cs);
+  tw[idx] = make_double2(cs, -sn);
 }
 
 inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
 
 int g_fft_config = -1;  // tuning hook (pt_debug_set_fft_config); -1 = choose by shape
 
-template <int LOG2N, bool STRIDED, int NT, int TILE>
+template <int LOG2N, bool STRIDED, int NT, int TILE, int TWS>
 int launch_fft_cfg(FftParams& p, cudaStream_t st) {
   using P = FftPlan<LOG2N, TILE>;
-  auto kern = fourier_fft_kernel<LOG2N, STRIDED, NT, TILE>;
+  constexpr size_t SMEM = P::SMEM + ((TWS & 1) ? size_t(P::N) * sizeof(double2) : 0);
+  auto kern = fourier_fft_kernel<LOG2N, STRIDED, NT, TILE, TWS>;
   static bool attr_set[64] = {false};
   int dev = 0;
   PT_CUDA(cudaGetDevice(&dev));
-  if (P::SMEM > 48 * 1024 && dev >= 0 && dev < 64 && !attr_set[dev]) {
-    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::SMEM)));
+  if (SMEM > 48 * 1024 && dev >= 0 && dev < 64 && !attr_set[dev]) {
+    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM)));
     attr_set[dev] = true;
   }
   if (STRIDED) {
@@ -372,21 +669,41 @@ int launch_fft_cfg(FftParams& p, cudaStream_t st) {
     p.groups_per_a = 1;
     p.ngroups = (p.after + 2 * P::S - 1) / (2 * P::S);
   }
-  int64_t grid = int64_t(pt::sm_count()) * (NT == 128 ? 5 : 2);
+  int64_t grid = int64_t(pt::sm_count()) * fft_min_ctas<NT, TWS>();
   if (grid > p.ngroups) grid = p.ngroups;
-  kern<<<unsigned(grid), NT, P::SMEM, st>>>(p);
+  kern<<<unsigned(grid), NT, SMEM, st>>>(p);
   return pt::check_launch("pt_fourier_apply");
 }
 
 template <int LOG2N, bool STRIDED>
 int launch_fft(FftParams& p, cudaStream_t st) {
-  // measured on B200 (tools/perf_probe.py fftcfg): 128 threads x 2048 points with 5 CTAs/SM wins for
-  // the contiguous n = 1024 axis (both BASELINE Fourier axes), 256 x 4096 with 2 CTAs/SM elsewhere
-  const int cfg = g_fft_config >= 0 ? g_fft_config : ((LOG2N == 10 && !STRIDED) ? 1 : 0);
-  switch (cfg) {
-    case 0: return launch_fft_cfg<LOG2N, STRIDED, 256, 4096>(p, st);
-    default: return launch_fft_cfg<LOG2N, STRIDED, 128, 2048>(p, st);
+  // Tuning ids (pt_debug_set_fft_config): 0/1 = 256x4096 / 128x2048 threads x points with the twiddles
+  // through L1; 3/4 = 128x2048 / 256x4096 with the table in shared memory; 5/11 = as 1/0 with derived
+  // twiddles; 8/9 = the warp-per-sequence kernel without / with the bulk-copy prefetch.
+  // Shared-memory twiddles need at least one shared round trip (n >= 32) and a table that leaves room
+  // for the tiles (n <= 2048).
+  constexpr bool CAN_TWS = LOG2N >= 5 && LOG2N <= 11;
+  // Defaults measured on B200 (tools/perf_probe.py fftcfg): contiguous axis: shared-memory
+  // twiddles up to n = 256, the warp kernel at n = 1024, derived twiddles through L1 elsewhere; strided
+  // axis: 256 x 4096 with shared-memory twiddles up to n = 1024, derived twiddles above.
+  constexpr int DEFAULT = LOG2N < 5 ? 0
+                          : !STRIDED ? (LOG2N <= 8 ? 3 : (LOG2N == 10 ? 8 : 5))
+                                     : (LOG2N <= 10 ? 4 : 11);
+  int cfg = g_fft_config >= 0 ? g_fft_config : DEFAULT;
+  if constexpr (LOG2N == 10 && !STRIDED) {
+    if (cfg == 9 && (reinterpret_cast<uintptr_t>(p.U) & 15)) cfg = 8;   // bulk copies need 16-byte alignment
+    if (cfg == 8) return launch_fft1024_warp<2, 8, false>(p, st);
+    if (cfg == 9) return launch_fft1024_warp<2, 8, true>(p, st);
   }
+  if (cfg == 8 || cfg == 9) cfg = 1;   // (the warp kernel exists for n = 1024 on the contiguous axis only)
+  if constexpr (CAN_TWS) {
+    if (cfg == 3) return launch_fft_cfg<LOG2N, STRIDED, 128, 2048, 3>(p, st);
+    if (cfg == 4) return launch_fft_cfg<LOG2N, STRIDED, 256, 4096, 3>(p, st);
+  }
+  if (cfg == 5) return launch_fft_cfg<LOG2N, STRIDED, 128, 2048, 2>(p, st);
+  if (cfg == 11) return launch_fft_cfg<LOG2N, STRIDED, 256, 4096, 2>(p, st);
+  if (cfg == 0 || cfg == 4) return launch_fft_cfg<LOG2N, STRIDED, 256, 4096, 0>(p, st);
+  return launch_fft_cfg<LOG2N, STRIDED, 128, 2048, 0>(p, st);
 }
 
 template <bool STRIDED>

@@ -134,3 +134,51 @@ def test_fft_after_scale_strided_axis():
     bound = oracle.abs_bound(D, U, F.npts, 1).reshape(after, n, before) * sc[:, None, None]
     got = F.apply(torch.from_numpy(U).cuda(), scale=sc, scale_mode="after").cpu().numpy().reshape(after, n, before)
     assert np.max(np.abs(got - ref) / bound) <= TOL
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("rows", [1, 2, 7, 300])
+def test_n1024_contiguous_warp_kernel(order, rows):
+    """n = 1024 on the contiguous axis runs the warp-per-sequence kernel: orders with a compile-time
+    symbol (1, 2) and the general one, odd row counts (the last row is paired with zeros), one row."""
+    if order > 2 and rows not in (7,):
+        pytest.skip("general-order symbol: one shape is enough")
+    _check(1024, order, (1024, rows), 0, 1, period=2.5)
+
+
+def test_n1024_contiguous_fused_scaling_accumulation_and_row_scale():
+    import torch
+
+    import pytristan_b200 as pt
+
+    _check(1024, 1, (1024, 9), 0, 2, alpha=1.5, beta=-0.25)
+    _check(1024, 2, (1024, 4), 0, 1, alpha=-2.0, beta=0.5)
+    n, rows = 1024, 13
+    x = np.arange(n) * (2 * np.pi / n)
+    F = pt.FourMat(x, order=2, method="fft")
+    F.npts, F.axis = (n, rows), 0
+    rng = np.random.default_rng(11)
+    U = rng.standard_normal((2, n * rows))
+    sc = rng.uniform(0.5, 2.0, rows)
+    D = oracle.four_mat(n, 2 * np.pi, 2)
+    ref = oracle.apply_along_axis(D, U, F.npts, 0).reshape(2, rows, n) * sc[None, :, None]
+    bound = oracle.abs_bound(D, U, F.npts, 0).reshape(2, rows, n) * sc[None, :, None]
+    got = F.apply(torch.from_numpy(U).cuda(), scale=sc, scale_mode="after").cpu().numpy().reshape(2, rows, n)
+    assert np.max(np.abs(got - ref) / bound) <= TOL
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 3, 4, 5, 8, 9, 11])
+def test_every_tuning_config_is_the_same_map(cfg):
+    """pt_debug_set_fft_config picks the kernel shape / twiddle source; every id must give the operator."""
+    from pytristan_b200 import _lib
+
+    lib = _lib.load()
+    try:
+        lib.pt_debug_set_fft_config(cfg)
+        _check(1024, 1, (1024, 11), 0, 1)
+        _check(1024, 2, (6, 1024, 2), 1, 1)
+        _check(256, 1, (256, 9), 0, 2)
+        _check(2048, 1, (2048, 3), 0, 1)
+        _check(64, 3, (10, 64, 3), 1, 1)
+    finally:
+        lib.pt_debug_set_fft_config(-1)

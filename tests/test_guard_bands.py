@@ -98,7 +98,8 @@ def test_stencil_kernels_stay_inside_their_fields(npts, axis, periodic, mapped):
     _check(ybuf, y, ref, bound, (npts, axis, periodic, mapped))
 
 
-@pytest.mark.parametrize("n,before,after", [(8, 1, 3), (64, 1, 5), (1024, 1, 7), (16, 6, 2), (256, 64, 2), (512, 2, 3)])
+@pytest.mark.parametrize("n,before,after", [(8, 1, 3), (64, 1, 5), (1024, 1, 7), (1024, 1, 1), (1024, 1, 1186), (16, 6, 2),
+                                            (256, 64, 2), (512, 2, 3), (1024, 4, 3), (2048, 1, 3), (2048, 2, 2)])
 def test_fft_kernel_stays_inside_its_fields(n, before, after):
     import pytristan_b200 as pt
 

@@ -194,10 +194,17 @@ if __name__ == "__main__":
         sys.exit(0)
     if what == "fftcfg":
         lib = _lib.load()
-        for cfg in (0, 1):
+        cfgs = [int(c) for c in sys.argv[2].split(",")] if len(sys.argv) > 2 else (0, 1, 2, 3, 4, 5, 6, 7, 8)
+        for cfg in cfgs:
             lib.pt_debug_set_fft_config(cfg)
             print("== fft config", cfg)
             fourier((1024, 257), 0, 64, "cfg2 d/dx FourMat n=1024 axis0")
+            if len(sys.argv) > 3:
+                continue
+            fourier((64, 65536), 0, 4, "n=64 axis0")
+            fourier((512, 8192), 0, 4, "n=512 axis0")
+            fourier((2048, 2048), 0, 4, "n=2048 axis0")
+            fourier((16, 2048, 64), 1, 4, "n=2048 axis1 before=16")
             fourier((256, 4096), 0, 16, "n=256 axis0")
             fourier((4096, 1024), 0, 4, "n=4096 axis0")
             fourier((64, 1024, 64), 1, 4, "n=1024 axis1 before=64")
