@@ -373,7 +373,6 @@ __global__ void __launch_bounds__(NT, fft_min_ctas<NT, TWS>()) fourier_fft_kerne
   }
 }
 
-// entry idx of the table: run L covers [n - L, n - L/4)
 
 // ---- n = 1024 on the contiguous axis: one warp per complex sequence, 1024 = 32 x 32 -------------
 // Lane j holds x[j + 32 q], q < 32, in registers and takes it through the radix-4, radix-4, radix-2
@@ -383,7 +382,9 @@ __global__ void __launch_bounds__(NT, fft_min_ctas<NT, TWS>()) fourier_fft_kerne
 // the stride-32 layout for the inverse levels 64, 256, 1024 and the stores.  Two shared round trips
 // instead of four, no CTA barrier (warps are independent and drift apart in phase, which is what
 // overlaps the loads of one with the butterflies of the others), a third of the twiddle loads.
-// The price is 32 complex numbers per thread: 168 registers, 12 warps per SM.
+// The price is 32 complex numbers per thread: 252 registers, 8 warps per SM (DESIGN.md 4.4 lists the
+// variants that were measured and lost: 12 warps at 168 registers, twiddles in shared memory, the next
+// row pair fetched into the tile by the bulk-copy engine or into L2 by prefetch instructions).
 
 __device__ __forceinline__ double cos32(int m) {   // cos(2 pi m / 32); m is a compile-time constant after unrolling
   m &= 31;
@@ -445,23 +446,12 @@ __device__ __forceinline__ double2 symbol_ks(double2 z, double ks, const FftPara
   }
 }
 
-__device__ __forceinline__ unsigned smem_addr(const void* ptr) { return unsigned(__cvta_generic_to_shared(ptr)); }
-// bounded wait (a pipeline bug must trap, not hang the GPU)
-__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, unsigned parity) {
-  asm volatile(
-      "{\n.reg .pred p, q;\n.reg .u32 spins;\nmov.u32 spins, 0;\n"
-      "FFT_WAIT: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra FFT_DONE;\n"
-      "add.u32 spins, spins, 1;\nsetp.gt.u32 q, spins, 4194304;\n@q trap;\nbra FFT_WAIT;\nFFT_DONE:\n}\n" ::"r"(smem_addr(bar)),
-      "r"(parity)
-      : "memory");
-}
-
-constexpr int W1K_WARPS = 1;                 // warps per CTA (warps are independent: no reason to tie them together)
+constexpr int W1K_WARPS = 4;                 // warps per CTA (independent of each other), 2 CTAs per SM
 constexpr int W1K_PITCH = 33 * 32;           // complex slots per warp tile: i + i/32
-constexpr size_t W1K_SMEM = size_t(W1K_WARPS) * W1K_PITCH * sizeof(double2) + 16;   // + the warp's mbarrier
+constexpr size_t W1K_SMEM = size_t(W1K_WARPS) * W1K_PITCH * sizeof(double2);
 
-template <int MODE, int ORDER, int CTAS, bool PF>
-__global__ void __launch_bounds__(W1K_WARPS * 32, CTAS) fourier_fft1024_warp_kernel(const FftParams p) {
+template <int MODE, int ORDER>
+__global__ void __launch_bounds__(W1K_WARPS * 32, 2) fourier_fft1024_warp_kernel(const FftParams p) {
   constexpr int N = 1024;
   extern __shared__ __align__(16) double2 fsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -472,29 +462,6 @@ __global__ void __launch_bounds__(W1K_WARPS * 32, CTAS) fourier_fft1024_warp_ker
   const int klow = (lane >> 3) + 4 * ((lane >> 1) & 3) + 16 * (lane & 1);
   const double ks_low = double(klow) * p.s;
   const bool drop_nyquist = klow == 0 && (p.order & 1);      // odd orders: the mode n/2 is dropped
-  // PF: the row pair of the warp's NEXT sequence is copied into the tile by the bulk-copy engine as soon as
-  // the last stage has read the tile, i.e. under that stage's butterflies and stores; the first stage
-  // then reads its inputs from shared memory instead of waiting on HBM.
-  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + W1K_WARPS * W1K_PITCH) + warp;
-  const double* raw = reinterpret_cast<const double*>(x);
-  auto fetch = [&](int64_t sq) {              // lane 0 only
-    const unsigned bytes = (2 * sq + 1 < p.after) ? 2 * N * 8 : N * 8;
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                     smem_addr(x)), "l"(p.U + 2 * sq * N), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-  };
-  unsigned phase = 0;
-  if (PF) {
-    if (lane == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(1));
-      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-      const int64_t first = int64_t(blockIdx.x) * W1K_WARPS + warp;
-      if (first < nseq) fetch(first);
-    }
-    __syncwarp();
-  }
 
   for (int64_t seq = int64_t(blockIdx.x) * W1K_WARPS + warp; seq < nseq; seq += int64_t(gridDim.x) * W1K_WARPS) {
     const int64_t r0 = 2 * seq;
@@ -507,16 +474,8 @@ __global__ void __launch_bounds__(W1K_WARPS * 32, CTAS) fourier_fft1024_warp_ker
     const double* __restrict__ u0 = p.U + r0 * N + lane;
     const double* __restrict__ u1 = u0 + (two ? N : 0);
     double2 v[32];
-    if (PF) {
-      mbar_wait_parity(bar, phase);
-      phase ^= 1;
-      const double* r1 = raw + (two ? N : 0);
 #pragma unroll
-      for (int q = 0; q < 32; ++q) { v[q].x = raw[lane + 32 * q]; v[q].y = r1[lane + 32 * q]; }
-    } else {
-#pragma unroll
-      for (int q = 0; q < 32; ++q) { v[q].x = u0[32 * q]; v[q].y = u1[32 * q]; }
-    }
+    for (int q = 0; q < 32; ++q) { v[q].x = u0[32 * q]; v[q].y = u1[32 * q]; }
     if (!two) {
 #pragma unroll
       for (int q = 0; q < 32; ++q) v[q].y = 0.0;
@@ -575,11 +534,6 @@ __global__ void __launch_bounds__(W1K_WARPS * 32, CTAS) fourier_fft1024_warp_ker
     // inverse levels 64, 256, 1024 on the elements lane + 32 q
 #pragma unroll
     for (int q = 0; q < 32; ++q) v[q] = x[lane + 33 * q];
-    if (PF) {
-      __syncwarp();                          // every lane has its elements: the tile is free for the next row pair
-      const int64_t nxt = seq + int64_t(gridDim.x) * W1K_WARPS;
-      if (lane == 0 && nxt < nseq) fetch(nxt);
-    }
     w64 = twiddle<MODE>(tw + (N - 64), ln);   // reloaded: cheaper than 4 registers held across the middle stage
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
@@ -610,9 +564,9 @@ __global__ void __launch_bounds__(W1K_WARPS * 32, CTAS) fourier_fft1024_warp_ker
   }
 }
 
-template <int MODE, int ORDER, int CTAS, bool PF>
+template <int ORDER>
 int launch_fft1024_warp_o(FftParams& p, cudaStream_t st) {
-  auto kern = fourier_fft1024_warp_kernel<MODE, ORDER, CTAS, PF>;
+  auto kern = fourier_fft1024_warp_kernel<2, ORDER>;
   static bool attr_set[64] = {false};
   int dev = 0;
   PT_CUDA(cudaGetDevice(&dev));
@@ -621,20 +575,20 @@ int launch_fft1024_warp_o(FftParams& p, cudaStream_t st) {
     attr_set[dev] = true;
   }
   const int64_t nseq = (p.after + 1) / 2;
-  int64_t grid = int64_t(pt::sm_count()) * CTAS;
+  int64_t grid = int64_t(pt::sm_count()) * 2;
   const int64_t need = (nseq + W1K_WARPS - 1) / W1K_WARPS;
   if (grid > need) grid = need;
   kern<<<unsigned(grid), W1K_WARPS * 32, W1K_SMEM, st>>>(p);
   return pt::check_launch("pt_fourier_apply");
 }
 
-template <int MODE, int CTAS, bool PF>
 int launch_fft1024_warp(FftParams& p, cudaStream_t st) {
-  if (p.order == 1) return launch_fft1024_warp_o<MODE, 1, CTAS, PF>(p, st);
-  if (p.order == 2) return launch_fft1024_warp_o<MODE, 2, CTAS, PF>(p, st);
-  return launch_fft1024_warp_o<MODE, 0, CTAS, PF>(p, st);
+  if (p.order == 1) return launch_fft1024_warp_o<1>(p, st);
+  if (p.order == 2) return launch_fft1024_warp_o<2>(p, st);
+  return launch_fft1024_warp_o<0>(p, st);
 }
 
+// entry idx of the table: run L covers [n - L, n - L/4)
 __global__ void twiddle_kernel(double2* tw, int n) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
@@ -679,7 +633,7 @@ template <int LOG2N, bool STRIDED>
 int launch_fft(FftParams& p, cudaStream_t st) {
   // Tuning ids (pt_debug_set_fft_config): 0/1 = 256x4096 / 128x2048 threads x points with the twiddles
   // through L1; 3/4 = 128x2048 / 256x4096 with the table in shared memory; 5/11 = as 1/0 with derived
-  // twiddles; 8/9 = the warp-per-sequence kernel without / with the bulk-copy prefetch.
+  // twiddles; 8 = the warp-per-sequence kernel.
   // Shared-memory twiddles need at least one shared round trip (n >= 32) and a table that leaves room
   // for the tiles (n <= 2048).
   constexpr bool CAN_TWS = LOG2N >= 5 && LOG2N <= 11;
@@ -691,11 +645,9 @@ int launch_fft(FftParams& p, cudaStream_t st) {
                                      : (LOG2N <= 10 ? 4 : 11);
   int cfg = g_fft_config >= 0 ? g_fft_config : DEFAULT;
   if constexpr (LOG2N == 10 && !STRIDED) {
-    if (cfg == 9 && (reinterpret_cast<uintptr_t>(p.U) & 15)) cfg = 8;   // bulk copies need 16-byte alignment
-    if (cfg == 8) return launch_fft1024_warp<2, 8, false>(p, st);
-    if (cfg == 9) return launch_fft1024_warp<2, 8, true>(p, st);
+    if (cfg == 8) return launch_fft1024_warp(p, st);
   }
-  if (cfg == 8 || cfg == 9) cfg = 1;   // (the warp kernel exists for n = 1024 on the contiguous axis only)
+  if (cfg == 8) cfg = 1;   // (the warp kernel exists for n = 1024 on the contiguous axis only)
   if constexpr (CAN_TWS) {
     if (cfg == 3) return launch_fft_cfg<LOG2N, STRIDED, 128, 2048, 3>(p, st);
     if (cfg == 4) return launch_fft_cfg<LOG2N, STRIDED, 256, 4096, 3>(p, st);
