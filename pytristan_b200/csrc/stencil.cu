@@ -588,13 +588,18 @@ __global__ void __launch_bounds__(TXT * TY, 1024 / (TXT * TY)) stencil_grad3_ker
 #pragma unroll
   for (int s = 0; s < W; ++s) { wx[s] = p.w[0][s]; wy[s] = p.w[1][s]; wz[s] = p.w[2][s]; }
 
+  // z window in registers; the plane that enters it is loaded one iteration before its first use (the
+  // centred dz stencil needs plane z + HW in iteration z: loaded in that iteration, the first DFMA of the
+  // dz sum waited on HBM — ncu: long_scoreboard on that DFMA was 10 % of all samples)
   double2 win[W];
 #pragma unroll
   for (int s = 0; s < W - 1; ++s) win[s] = ldz(z0 - HW + s);
+  double2 ahead = ldz(z0 + HW);
   double2 hreg = (h_ok) ? *reinterpret_cast<const double2*>(p.U + z0 * plane + h_off) : zero2;
 
   for (int z = z0; z < z1; ++z) {
-    win[W - 1] = ldz(z + HW);
+    win[W - 1] = ahead;
+    ahead = (z + 1 < z1) ? ldz(z + 1 + HW) : zero2;
     double* buf = sm[z & 1];
     *reinterpret_cast<double2*>(buf + (ty + HW) * PITCH + HX + 2 * tx) = win[HW];
     if (h_sm >= 0) {
@@ -607,7 +612,8 @@ __global__ void __launch_bounds__(TXT * TY, 1024 / (TXT * TY)) stencil_grad3_ker
       double v[10];
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const double2 t2 = *reinterpret_cast<const double2*>(rowp + 2 * k);
+        // (the pair in the middle is this thread's own: it is in the z window already)
+        const double2 t2 = (2 * k == HX) ? win[HW] : *reinterpret_cast<const double2*>(rowp + 2 * k);
         v[2 * k] = t2.x; v[2 * k + 1] = t2.y;
       }
       double2 gx2 = zero2, gy2 = zero2, gz2 = zero2;

@@ -259,6 +259,21 @@ if __name__ == "__main__":
             dense((512, 512, 512), 0, 1, "cfg5b x K2 n=512")
             dense((512, 512, 512), 1, 1, "cfg5b y K1 n=512")
         lib.pt_debug_set_dense_config(0)
+    if what == "grad":
+        import ctypes
+        _l = _lib.load(); _l.pt_debug_set_grad_ty.argtypes = [ctypes.c_int]
+        for n, ty in ((1024, 108), (1024, 116), (512, 108)):
+            _l.pt_debug_set_grad_ty(ty)
+            ops = []
+            for k in range(3):
+                F = pt.FinDiffMat(np.linspace(0, 1, n), order=1, accuracy=6); F.npts, F.axis = (n, n, n), k; ops.append(F)
+            U = torch.randn(n ** 3, dtype=torch.float64, device="cuda"); outs = [torch.empty_like(U) for _ in range(3)]
+            pt.gradient(ops, U, outs=outs)
+            ms = timeit(lambda: pt.gradient(ops, U, outs=outs))
+            print(json.dumps({"case": f"fused gradient {n}^3 tile={ty}", "ms": round(ms, 4), "gbs_32B": round(32.0 * n ** 3 / ms * 1e-6, 1),
+                              "frac_hbm": round(32.0 * n ** 3 / ms * 1e-6 / HBM, 3), "gpts_s_x3": round(3 * n ** 3 / ms * 1e-6, 2)}))
+            del U, outs
+        sys.exit(0)
     if what in ("dense", "all"):
         dense((1024, 257), 0, 64, "cfg2 d/dx K2 n=1024")
         dense((1024, 257), 1, 64, "cfg2 d2/dy2 K1 n=257")
