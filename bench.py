@@ -968,6 +968,10 @@ def extra_workloads(ctx, args, threads, recs):
             spec = workload_spec(name)
 
             def one(spec=spec):
+                # a second of idle first: the power-cap window of the workload before must not be charged to this one
+                # (seen: sw_power_cap at 1680 MHz on a 20 ms polar measurement that followed the 1024^3 slabs)
+                torch.cuda.synchronize()
+                time.sleep(1.0)
                 m = measure_plain(ctx, spec, steps, 3, e2e=False, graph=spec["name"].endswith("_b1"))
                 r0 = m["ranks"][0]
                 ms = r0["ms_per_step"]
