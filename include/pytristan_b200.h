@@ -173,7 +173,10 @@ int pt_dense_apply_eo_ws(const double* packed_ws, int n, int sign, const double*
                          int scale_mode, int64_t scale_len, pt_stream_t stream);
 
 /* ---- FourMat through the FFT ----------------------------------------- */
-/* tw[2*m], tw[2*m+1] = cos, -sin of 2 pi m / n for m < n (n complex doubles); n a power of two. */
+/* Twiddle table of pt_fourier_apply: n complex doubles (2 n doubles), n a power of two.  Opaque to the
+ * caller; the layout is one run of roots of unity per radix-4 level L = n, n/4, n/16, ...:
+ * tw[n - L + i] = exp(-2 pi i * i / L) for i < 3L/4, so that neighbouring lanes read neighbouring entries
+ * at every level.  Build it once per n with this call and keep it with the operator. */
 int pt_fourier_twiddles(int n, double* tw, pt_stream_t stream);
 /* Y[a,:,b] = alpha * scale[a % scale_len] * (D U[a,:,b]) + beta * Y[a,:,b] (scale may be NULL:
  * no scaling; it is the PT_SCALE_AFTER epilogue of pt_dense_apply) with D the order-`order` Fourier spectral
