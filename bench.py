@@ -964,7 +964,7 @@ def extra_workloads(ctx, args, threads, recs):
         guarded(f"{name}/{comm}", lambda: measure_sharded(ctx, spec, comm, steps, 3, fused=fused))
     if ctx.world == 1:
         for name in ("polar_1024x512_b64", "polar_1024x512_b1", "fd6_1024cube", "fd6_1024cube_grad3", "cheb2048_b65536",
-                     "channel_1024x257_b64_fft"):
+                     "channel_1024x257_b64_fft", "polar_1024x512_b64_fft"):
             spec = workload_spec(name)
 
             def one(spec=spec):
