@@ -327,6 +327,32 @@ int pt_replace_rows(double* D, int n, const int32_t* rows, int nrows, const doub
 int64_t pt_invert_work_size(int n);
 int pt_invert(const double* A, int n, double* Ainv, double* work, int32_t* info, pt_stream_t stream);
 
+/* pt_dense_apply (no scaling) on ROW RANGES along the axis of longer fields: ldu / ldy are the distances in
+ * doubles between consecutive `a` slabs of U and Y (n_in*before / n_out*before for whole fields); U and Y point
+ * at the first row of the range.  The building block of the block substitutions below. */
+int pt_dense_apply_ld(const double* packed, int n_out, int n_in, const double* U, int64_t ldu, double* Y,
+                      int64_t ldy, int64_t after, int64_t before, double alpha, double beta, pt_stream_t stream);
+
+/* Factorisation-based solve along an axis: P A = L U, then blocked substitution.
+ * pt_lu_factor: LU (n*n row-major, may alias A) receives the multipliers of the unit lower factor below the
+ *   diagonal and U on and above it; perm[i] = row of A that is row i of P A; partial pivoting with the first
+ *   row of maximal modulus (LAPACK's rule); work: pt_lu_work_size(n) doubles; *info (device int32) = c+1 if
+ *   column c has no nonzero pivot, else 0.  n <= 8192.
+ * pt_lu_plan: for block rows of nb rows (multiple of 16, <= 128) packs the off-diagonal block rows L[b, 0:r0] and
+ *   U[b, r0+m:n] as pt_operator_pack operators and the diagonal triangles for the substitution kernel into plan
+ *   (pt_lu_plan_size doubles).
+ * pt_lu_solve: X[a, :, b] = A^-1 F[a, :, b] for every grid line: one row-permuting copy, then per block row one
+ *   rectangular pt_dense_apply_ld (tensor cores: all of the O(n^2) work per line) and one triangular
+ *   substitution with the nb*nb diagonal block (FP64 FMA, one thread per grid line — never a product with an
+ *   inverted block: componentwise backward stable) in the forward and in the backward sweep.  work is a second
+ *   field-sized buffer; F, X and work are distinct.  Nothing is allocated, nothing synchronises. */
+int64_t pt_lu_work_size(int n);
+int pt_lu_factor(const double* A, int n, double* LU, int32_t* perm, double* work, int32_t* info, pt_stream_t stream);
+int64_t pt_lu_plan_size(int n, int nb);
+int pt_lu_plan(const double* LU, int n, int nb, double* plan, pt_stream_t stream);
+int pt_lu_solve(const double* plan, const int32_t* perm, int n, int nb, const double* F, double* X, double* work,
+                int64_t after, int64_t before, pt_stream_t stream);
+
 /* ---- measurement helper ------------------------------------------------------------------ */
 /* Register-resident DMMA loop: the FP64 tensor-core roofline denominator measured on the box.
  * Writes achieved TFLOP/s to *tflops_host. */

@@ -421,3 +421,33 @@ def polar_laplacian(theta, r, U):
     T = apply_along_axis(D2t, U, (nt, nr), 0)
     scale = np.tile(np.repeat(1.0 / (r * r), nt), U.size // (nt * nr)).reshape(U.shape)
     return Y + scale * T
+
+
+# ---- solves along an axis (no reference code exists: textbook LU, Golub & Van Loan
+# Alg. 3.4.1, pinned in tests/test_oracle.py against scipy.linalg.lu_factor / numpy.linalg.solve) ------------
+def lu_factor(A):
+    """P A = L U by Gaussian elimination with partial pivoting (first row of maximal modulus).  Returns
+    (perm, LU): A[perm] = L @ U with L = tril(LU, -1) + I and U = triu(LU)."""
+    LU = np.array(A, dtype=np.float64)
+    n = LU.shape[0]
+    perm = np.arange(n)
+    for c in range(n):
+        p = c + int(np.argmax(np.abs(LU[c:, c])))
+        if LU[p, c] == 0.0:
+            raise np.linalg.LinAlgError(f"singular matrix (elimination step {c})")
+        if p != c:
+            LU[[c, p]] = LU[[p, c]]
+            perm[[c, p]] = perm[[p, c]]
+        LU[c + 1:, c] /= LU[c, c]
+        LU[c + 1:, c + 1:] -= np.outer(LU[c + 1:, c], LU[c, c + 1:])
+    return perm, LU
+
+
+def solve_along_axis(A, F, npts, axis):
+    """Y with A @ Y[a, :, b] = F[a, :, b] on the (after, n, before) view of the flat field(s) F
+    (numpy.linalg.solve = LAPACK gesv on all grid lines at once)."""
+    F = np.asarray(F, dtype=np.float64)
+    after, n, before = axis_split(npts, axis, F.size)
+    V = F.reshape(after, n, before).transpose(1, 0, 2).reshape(n, -1)
+    Y = np.linalg.solve(np.asarray(A, dtype=np.float64), V)
+    return Y.reshape(n, after, before).transpose(1, 0, 2).reshape(F.shape)

@@ -112,6 +112,12 @@ SIGNATURES = {
     "pt_replace_rows": (_c_i32, [_c_ptr, _c_i32, _c_ptr, _c_i32, _c_ptr, _c_ptr]),
     "pt_invert_work_size": (_c_i64, [_c_i32]),
     "pt_invert": (_c_i32, [_c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+    "pt_dense_apply_ld": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_i64, _c_ptr, _c_i64, _c_i64, _c_i64, _c_f64, _c_f64, _c_ptr]),
+    "pt_lu_work_size": (_c_i64, [_c_i32]),
+    "pt_lu_factor": (_c_i32, [_c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+    "pt_lu_plan_size": (_c_i64, [_c_i32, _c_i32]),
+    "pt_lu_plan": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr]),
+    "pt_lu_solve": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr]),
     "pt_measure_dmma_peak": (_c_i32, [ctypes.POINTER(_c_f64), _c_i32]),
     "pt_peer_alloc": (_c_i32, [_c_i64, ctypes.POINTER(_c_ptr)]),
     "pt_peer_free": (_c_i32, [_c_ptr]),

@@ -170,7 +170,7 @@ dense_apply_kernel(const DenseParams p) {
         const int col = b_r0 + r * RPP2;
         const int64_t nn = n0 + col;
         const bool ok = (nn < p.NN) && (k < p.n_in);
-        const double* src = ok ? p.U + nn * p.n_in + k : p.U;
+        const double* src = ok ? p.U + nn * p.slab_in + k : p.U;
         double* dst = Bs + col * C::PB + b_cc * EPC;
         if (VEC16) {
           const int bytes = ok ? ((k + 1 < p.n_in) ? 16 : 8) : 0;
@@ -202,8 +202,8 @@ dense_apply_kernel(const DenseParams p) {
     b_rstep = int64_t(RPP1) * p.before;
     b_ok = b_col_ok ? ~0u : 0u;
   } else {
-    b_ptr = p.U + (n0 + b_r0) * p.n_in + b_cc * EPC;
-    b_rstep = int64_t(RPP2) * p.n_in;
+    b_ptr = p.U + (n0 + b_r0) * p.slab_in + b_cc * EPC;
+    b_rstep = int64_t(RPP2) * p.slab_in;
 #pragma unroll
     for (int r = 0; r < C::BN / RPP2; ++r)
       if (n0 + b_r0 + r * RPP2 < p.NN) b_ok |= 1u << r;
@@ -460,19 +460,22 @@ extern "C" int pt_operator_pack(const double* D, int n_out, int n_in, int64_t ld
   return pt::check_launch("pt_operator_pack");
 }
 
-extern "C" int pt_dense_apply(const double* packed, int n_out, int n_in, const double* U, double* Y,
-                              int64_t after, int64_t before, double alpha, double beta,
-                              const double* scale, int scale_mode, int64_t scale_len,
-                              pt_stream_t stream) {
-  PT_REQUIRE(packed && U && Y, "pt_dense_apply: null pointer");
-  PT_REQUIRE(n_out > 0 && n_in > 0, "pt_dense_apply: bad operator shape %d x %d", n_out, n_in);
-  PT_REQUIRE(after >= 0 && before >= 1, "pt_dense_apply: bad field shape after=%lld before=%lld",
+// Shared body of pt_dense_apply / pt_dense_apply_ld: ldu, ldy = distance in doubles between consecutive
+// `a` slabs of U and Y (n_in*before and n_out*before for whole fields; larger when U / Y are row ranges
+// along the axis of a longer field, as in the block substitutions of pt_lu_solve).
+static int dense_apply_impl(const char* who, const double* packed, int n_out, int n_in, const double* U, int64_t ldu,
+                            double* Y, int64_t ldy, int64_t after, int64_t before, double alpha, double beta,
+                            const double* scale, int scale_mode, int64_t scale_len, pt_stream_t stream) {
+  PT_REQUIRE(packed && U && Y, "%s: null pointer", who);
+  PT_REQUIRE(n_out > 0 && n_in > 0, "%s: bad operator shape %d x %d", who, n_out, n_in);
+  PT_REQUIRE(after >= 0 && before >= 1, "%s: bad field shape after=%lld before=%lld", who,
              (long long)after, (long long)before);
-  PT_REQUIRE(scale_mode >= PT_SCALE_NONE && scale_mode <= PT_SCALE_BEFORE,
-             "pt_dense_apply: bad scale_mode %d", scale_mode);
-  PT_REQUIRE(scale_mode == PT_SCALE_NONE || scale != nullptr, "pt_dense_apply: scale is null");
-  PT_REQUIRE(scale_mode != PT_SCALE_AFTER || scale_len > 0, "pt_dense_apply: scale_len must be > 0");
-  PT_REQUIRE(U != Y, "pt_dense_apply: in-place application is not supported");
+  PT_REQUIRE(ldu >= int64_t(n_in) * before && ldy >= int64_t(n_out) * before, "%s: slab strides %lld / %lld too small",
+             who, (long long)ldu, (long long)ldy);
+  PT_REQUIRE(scale_mode >= PT_SCALE_NONE && scale_mode <= PT_SCALE_BEFORE, "%s: bad scale_mode %d", who, scale_mode);
+  PT_REQUIRE(scale_mode == PT_SCALE_NONE || scale != nullptr, "%s: scale is null", who);
+  PT_REQUIRE(scale_mode != PT_SCALE_AFTER || scale_len > 0, "%s: scale_len must be > 0", who);
+  PT_REQUIRE(U != Y, "%s: in-place application is not supported", who);
   if (after == 0) return PT_OK;
 
   DenseParams p;
@@ -483,18 +486,33 @@ extern "C" int pt_dense_apply(const double* packed, int n_out, int n_in, const d
   p.KP = (n_in + 3) / 4;
   p.before = before;
   p.NN = after * before;
-  p.slab_in = int64_t(n_in) * before;
-  p.slab_out = int64_t(n_out) * before;
+  p.slab_in = ldu;
+  p.slab_out = ldy;
   p.alpha = alpha; p.beta = beta;
   p.scale_mode = scale_mode; p.scale_len = scale_len > 0 ? scale_len : 1;
   p.m_blocks = 1; p.mt_per_block = 1;
   cudaStream_t st = pt::as_stream(stream);
   if (before == 1) {
-    const bool vec = (n_in % 2 == 0) && aligned16(U);
+    const bool vec = (n_in % 2 == 0) && (ldu % 2 == 0) && aligned16(U);
     return vec ? launch_shape<true, true>(p, st) : launch_shape<true, false>(p, st);
   }
-  const bool vec = (before % 2 == 0) && aligned16(U) && aligned16(Y);
+  const bool vec = (before % 2 == 0) && (ldu % 2 == 0) && (ldy % 2 == 0) && aligned16(U) && aligned16(Y);
   return vec ? launch_shape<false, true>(p, st) : launch_shape<false, false>(p, st);
+}
+
+extern "C" int pt_dense_apply(const double* packed, int n_out, int n_in, const double* U, double* Y,
+                              int64_t after, int64_t before, double alpha, double beta,
+                              const double* scale, int scale_mode, int64_t scale_len,
+                              pt_stream_t stream) {
+  return dense_apply_impl("pt_dense_apply", packed, n_out, n_in, U, int64_t(n_in) * before, Y, int64_t(n_out) * before,
+                          after, before, alpha, beta, scale, scale_mode, scale_len, stream);
+}
+
+extern "C" int pt_dense_apply_ld(const double* packed, int n_out, int n_in, const double* U, int64_t ldu, double* Y,
+                                 int64_t ldy, int64_t after, int64_t before, double alpha, double beta,
+                                 pt_stream_t stream) {
+  return dense_apply_impl("pt_dense_apply_ld", packed, n_out, n_in, U, ldu, Y, ldy, after, before, alpha, beta, nullptr,
+                          PT_SCALE_NONE, 1, stream);
 }
 
 // ---- dense apply fused with the pencil redistribution (scatter epilogue over peer memory) -------

@@ -255,3 +255,33 @@ def test_operator_known_answer_vectors_are_stable():
     assert sorted(frozen.files) == sorted(now)
     for key in frozen.files:
         assert frozen[key].dtype == now[key].dtype and np.array_equal(frozen[key], now[key]), key
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 40, 129])
+def test_lu_oracle_vs_lapack(n):
+    """oracle.lu_factor (textbook partial pivoting) against LAPACK getrf through scipy, and
+    oracle.solve_along_axis against a Kronecker-lifted dense solve."""
+    import scipy.linalg as sla
+
+    rng = np.random.default_rng(100 + n)
+    A = rng.standard_normal((n, n))
+    A[0, 0] = 0.0 if n > 1 else 1.0                      # forces a row exchange in the first step
+    perm, LU = oracle.lu_factor(A)
+    L, U = np.tril(LU, -1) + np.eye(n), np.triu(LU)
+    assert sorted(perm.tolist()) == list(range(n))
+    assert np.max(np.abs(L)) <= 1.0
+    assert np.max(np.abs(A[perm] - L @ U)) <= 4 * n * np.finfo(float).eps * np.max(np.abs(L) @ np.abs(U))
+    lu_ref, piv = sla.lu_factor(A)
+    perm_ref = np.arange(n)
+    for c, p in enumerate(piv):
+        perm_ref[[c, p]] = perm_ref[[p, c]]
+    assert np.array_equal(perm, perm_ref)
+    assert np.max(np.abs(LU - lu_ref)) <= 1e-12 * np.max(np.abs(lu_ref)) * max(1.0, np.linalg.cond(A)) ** 0.5
+    if n >= 7:
+        npts = (3, n, 2)
+        F = rng.standard_normal((2, 6 * n))
+        Y = oracle.solve_along_axis(A, F, npts, 1)
+        back = oracle.apply_along_axis(A, Y, npts, 1)
+        assert np.max(np.abs(back - F)) <= 1e-12 * np.linalg.cond(A) * np.max(np.abs(F))
+    with pytest.raises(np.linalg.LinAlgError):
+        oracle.lu_factor(np.ones((3, 3)))

@@ -126,8 +126,37 @@ def eo_variants(kind, n, order, npts, axis, batch, label, which=(True, False)):
     del ring, Y
 
 
+def solve_probe(n, npts, axis, batch, label, blocks=(32, 64, 128)):
+    """AxisSolver: one pass with the explicit inverse against the blocked LU substitution (executed flops of the
+    LU form: n^2 per line for the two triangles, x2 for FMA)."""
+    x = pt.cheb(n, -1.0, 1.0)
+    A = pt.dirichlet(pt.ChebMat(x, order=2))
+    P = int(np.prod(npts))
+    F = torch.randn(batch, P, dtype=torch.float64, device="cuda")
+    Y = torch.empty_like(F)
+    inv = pt.AxisSolver(A, npts=npts, axis=axis, method="inverse")
+    ms = timeit(lambda: inv.solve(F, out=Y))
+    lines = P * batch / n
+    print(json.dumps({"case": label + " inverse", "ms": round(ms, 4), "tflops": round(2.0 * n * n * lines / ms * 1e-9, 2)}))
+    for blk in blocks:
+        t0 = time.perf_counter()
+        lu = pt.AxisSolver(A, npts=npts, axis=axis, block=blk)
+        torch.cuda.synchronize()
+        setup = time.perf_counter() - t0
+        ms = timeit(lambda: lu.solve(F, out=Y))
+        fl = 2.0 * n * n * lines
+        print(json.dumps({"case": label + f" lu block={blk}", "ms": round(ms, 4), "tflops_executed": round(fl / ms * 1e-9, 2),
+                          "frac_fp64_peak": round(fl / ms * 1e-9 / PEAK_TF, 3), "setup_s": round(setup, 3)}))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "solve":
+        solve_probe(257, (1024, 257), 1, 64, "cfg2 y-solve n=257 (strided axis)")
+        solve_probe(1024, (1024, 257), 0, 64, "cfg2 x-solve n=1024 (contiguous axis)")
+        solve_probe(512, (512, 512, 512), 1, 1, "512^3 y-solve n=512")
+        solve_probe(2048, (8192, 2048), 1, 1, "n=2048 8192 lines", blocks=(64, 128))
+        sys.exit(0)
     if what == "wsdbg":
         lib = _lib.load()
         for mode in (1, 6, 1, 6):
