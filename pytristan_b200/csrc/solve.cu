@@ -11,7 +11,7 @@
 // the off-diagonal block rows of L and U and the inverted nb x nb diagonal blocks are packed operators
 // applied by pt_dense_apply_ld to row ranges of the fields (the scheme of a GPU TRSM), so the solve
 // never forms A^-1 and never transposes or repacks a field.
-#include "common.cuh"
+#include "dense_common.cuh"
 
 namespace {
 
@@ -200,13 +200,17 @@ __global__ void tri_pack_kernel(const double* __restrict__ LU, int n, int r0, in
 //   (1) rows s0..s0+15 -= T[s0.., 0:s0] x[0:s0] for its 32 lines as a 16 x s0 x 32 product on the FP64 tensor cores
 //       (DMMA m8n8k4 accumulating onto the rows themselves: A fragments of the negated triangle straight from L1,
 //       B fragments from the tile, pitch = 4 mod 16);
-//   (2) the 16 x 16 triangle by one thread per line in registers (120 FMAs; the entries are warp-uniform loads).
+//   (2) the 16 x 16 triangle by one thread per line in registers (120 FMAs);
+//   the rows of the triangle a sub-block needs arrive by cp.async in a double-buffered panel one sub-block ahead.
 // Only warp barriers in the loop.  128 lines = 4 warps per CTA and ONE CTA per SM (the tile of a 128-row block
 // fills it): a warp issuing plain FP64 instructions beside a warp that streams DMMAs on the same sub-partition
 // waits ~150 cycles per instruction for the pipe, so every sub-partition hosts exactly one warp.  In/Out address element (line nn, row r) at
 // (nn / before) * ld + r * before + nn % before; `reversed` mirrors the row order (upper factor).
 constexpr int TRI_TL = 128;
 constexpr int TRI_TLP = TRI_TL + 4;
+constexpr int TRI_PP = 20;                    // pitch of a staged triangle panel row (16 entries), = 4 mod 16
+constexpr int TRI_PANEL = 128 * TRI_PP;       // doubles of one panel buffer (up to 128 k rows)
+constexpr int TRI_MAXM = 128;
 
 __device__ __forceinline__ void tri_dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -219,31 +223,35 @@ __global__ void __launch_bounds__(TRI_TL) tri_solve_kernel(const double* __restr
                                                            const double* __restrict__ In, int64_t ld_in,
                                                            double* __restrict__ Out, int64_t ld_out, int64_t NN,
                                                            int64_t before) {
-  extern __shared__ __align__(16) double tile[];   // [m16][TRI_TLP]
+  extern __shared__ __align__(16) double tile[];   // [m16][TRI_TLP], then two panel buffers
+  double* panels = tile + m16 * TRI_TLP;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int L0 = (tid >> 5) * 32;
   const int64_t n0 = int64_t(blockIdx.x) * TRI_TL;
-  // loads in batches of 8 independent requests per thread (a dependent one-per-iteration loop costs a DRAM latency each)
+
+  // rows of the triangle that sub-block s0 needs: TT[k][s0 .. s0+15] for k < s0 + 16 (the last 16 k are the
+  // 16 x 16 triangle itself) — 16-byte cp.async into panel buffer (s0 / 16) & 1
+  auto issue_panel = [&](int s0) {
+    double* pan = panels + ((s0 >> 4) & 1) * TRI_PANEL;
+    const int pieces = (s0 + 16) * 8;
+    for (int pc = tid; pc < pieces; pc += TRI_TL) {
+      const int k = pc >> 3, c = (pc & 7) * 2;
+      ptdense::cp_async16(pan + k * TRI_PP + c, TT + int64_t(k) * m16 + s0 + c, 16);
+    }
+  };
+
+  // the whole tile asynchronously (8-byte copies: the tile transposes / strides), zero padding by plain stores
   if (before == 1) {
-    // lines are rows of memory: a thread walks 8 lines at the same row offset; consecutive threads take consecutive rows
-    const int rows_per_pass = TRI_TL;                       // consecutive threads = consecutive rows of one line
-    for (int row0 = 0; row0 < m16; row0 += rows_per_pass) {
-      const int row = row0 + tid;
-      const bool row_ok = row < m;
+    // lines are rows of memory: consecutive threads take consecutive rows of one line
+    for (int row = tid; row < m16; row += TRI_TL) {
       const int ar = reversed ? m - 1 - row : row;
-      for (int l0 = 0; l0 < TRI_TL; l0 += 8) {
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int64_t nn = n0 + l0 + u;
-          v[u] = (row_ok && nn < NN) ? In[nn * ld_in + ar] : 0.0;
-        }
-        if (row < m16) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) tile[row * TRI_TLP + l0 + u] = v[u];
-        }
+      for (int line = 0; line < TRI_TL; ++line) {
+        const int64_t nn = n0 + line;
+        double* dst = tile + row * TRI_TLP + line;
+        if (row < m && nn < NN) ptdense::cp_async8(dst, In + nn * ld_in + ar, 8);
+        else *dst = 0.0;
       }
     }
   } else {
@@ -251,20 +259,22 @@ __global__ void __launch_bounds__(TRI_TL) tri_solve_kernel(const double* __restr
     const int64_t a = nn / before;
     const double* src = In + a * ld_in + (nn - a * before);
     const bool ok = nn < NN;
-    for (int row0 = 0; row0 < m16; row0 += 8) {
-      double v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int row = row0 + u;
-        v[u] = (ok && row < m) ? src[int64_t(reversed ? m - 1 - row : row) * before] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) tile[(row0 + u) * TRI_TLP + tid] = v[u];
+    for (int row = 0; row < m16; ++row) {
+      double* dst = tile + row * TRI_TLP + tid;
+      if (ok && row < m) ptdense::cp_async8(dst, src + int64_t(reversed ? m - 1 - row : row) * before, 8);
+      else *dst = 0.0;
     }
   }
-  __syncthreads();
+  issue_panel(0);
+  ptdense::cp_async_commit();
+
   double* col = tile + tid;
   for (int s0 = 0; s0 < m16; s0 += 16) {
+    ptdense::cp_async_wait<0>();
+    __syncthreads();                       // panel s0 (and the tile) landed; everyone is done with the other buffer
+    if (s0 + 16 < m16) issue_panel(s0 + 16);
+    ptdense::cp_async_commit();
+    const double* pan = panels + ((s0 >> 4) & 1) * TRI_PANEL;
     if (s0 > 0) {
       double acc[2][4][2];
       // C fragment: row = s0 + 8 i + g, lines L0 + 8 j + 2 t4, +1 — the accumulators start as the rows themselves
@@ -275,21 +285,20 @@ __global__ void __launch_bounds__(TRI_TL) tri_solve_kernel(const double* __restr
           const double2 v = *reinterpret_cast<const double2*>(tile + (s0 + 8 * i + g) * TRI_TLP + L0 + 8 * j + 2 * t4);
           acc[i][j][0] = v.x; acc[i][j][1] = v.y;
         }
-      const double* ap = TT + int64_t(t4) * m16 + s0 + g;          // A[row = s0 + 8 i + g][k = k0 + t4] = TT[k][row] = -T
+      const double* ap = pan + t4 * TRI_PP + g;                     // A[row = s0 + 8 i + g][k = k0 + t4] = -T
       const double* bp = tile + t4 * TRI_TLP + L0 + g;              // B[k = k0 + t4][line = L0 + 8 j + g]
-      double a0 = __ldg(ap), a1 = __ldg(ap + 8);
+#pragma unroll 2
       for (int k0 = 0; k0 < s0; k0 += 4) {
-        ap += 4 * int64_t(m16);
-        const double c0 = a0, c1 = a1;
-        if (k0 + 4 < s0) { a0 = __ldg(ap); a1 = __ldg(ap + 8); }   // next panel's fragments under this panel's DMMAs
+        const double a0 = ap[0], a1 = ap[8];
         double bf[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) bf[j] = bp[8 * j];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          tri_dmma(acc[0][j][0], acc[0][j][1], c0, bf[j]);
-          tri_dmma(acc[1][j][0], acc[1][j][1], c1, bf[j]);
+          tri_dmma(acc[0][j][0], acc[0][j][1], a0, bf[j]);
+          tri_dmma(acc[1][j][0], acc[1][j][1], a1, bf[j]);
         }
+        ap += 4 * TRI_PP;
         bp += 4 * TRI_TLP;
       }
 #pragma unroll
@@ -303,13 +312,13 @@ __global__ void __launch_bounds__(TRI_TL) tri_solve_kernel(const double* __restr
     double t[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) t[r] = col[(s0 + r) * TRI_TLP];
+    const double* tri = pan + s0 * TRI_PP;                           // the 16 x 16 triangle: tri[r * PP + r2] = -T[s0+r2][s0+r]
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-      const double* tc = TT + int64_t(s0 + r) * m16 + s0;
-      const double x = UNIT ? t[r] : t[r] * __ldg(tc + r);
+      const double x = UNIT ? t[r] : t[r] * tri[r * TRI_PP + r];
       t[r] = x;
 #pragma unroll
-      for (int r2 = r + 1; r2 < 16; ++r2) t[r2] = fma(__ldg(tc + r2), x, t[r2]);
+      for (int r2 = r + 1; r2 < 16; ++r2) t[r2] = fma(tri[r * TRI_PP + r2], x, t[r2]);
     }
 #pragma unroll
     for (int r = 0; r < 16; ++r) col[(s0 + r) * TRI_TLP] = t[r];
@@ -317,9 +326,7 @@ __global__ void __launch_bounds__(TRI_TL) tri_solve_kernel(const double* __restr
   }
   __syncthreads();
   if (before == 1) {
-    for (int row0 = 0; row0 < m; row0 += TRI_TL) {
-      const int row = row0 + tid;
-      if (row >= m) break;
+    for (int row = tid; row < m; row += TRI_TL) {
       const int ar = reversed ? m - 1 - row : row;
       for (int line = 0; line < TRI_TL; ++line) {
         const int64_t nn = n0 + line;
@@ -481,12 +488,12 @@ template <bool UNIT>
 int launch_tri_solve(const double* TT, const LuBlock& k, int reversed, const double* in, double* out, int64_t ld,
                      int64_t after, int64_t before, cudaStream_t st) {
   auto kern = tri_solve_kernel<UNIT>;
-  const size_t smem = size_t(k.m16) * TRI_TLP * sizeof(double);
+  const size_t smem = (size_t(k.m16) * TRI_TLP + 2 * TRI_PANEL) * sizeof(double);
   static bool attr_set[64] = {false};
   int dev = 0;
   PT_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(128) * TRI_TLP * sizeof(double))));
+    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int((size_t(TRI_MAXM) * TRI_TLP + 2 * TRI_PANEL) * sizeof(double))));
     attr_set[dev] = true;
   }
   const int64_t NN = after * before;
