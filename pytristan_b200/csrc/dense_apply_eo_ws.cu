@@ -494,8 +494,24 @@ __global__ void __launch_bounds__(NT, 1) dense_apply_eo_ws_kernel(const EoParams
       }
     }
     if (tracing) tr[7] = clock64();                              // middle row stored
-    eo_epilogue<WR, WN, KCONTIG, true, SCAT, MIDFIX>(p, acce, acco, my_rt, rt0 * 8 + my_rt0 * 8, n0 + wn * WN * 8, g, t,
-                                                     cmid_s, umid_s + (ti & 1) * BN + wn * WN * 8);
+    if (MIDFIX) {
+      // middle column: ze[i][col] += D[i][mid] * u[mid][col] as ONE DMMA per accumulator tile — an outer product
+      // whose k = 1..3 terms are zero — instead of two FMAs per element in the epilogue: a plain FP64 instruction
+      // issued here queues behind the DMMAs of the warp that shares the sub-partition, a DMMA takes its turn
+      const double* um = umid_s + (ti & 1) * BN + wn * WN * 8;
+      const double* cm = cmid_s + rt0 * 8 + my_rt0 * 8;
+      double bm[WN];
+#pragma unroll
+      for (int j = 0; j < WN; ++j) bm[j] = t == 0 ? um[j * 8 + g] : 0.0;
+#pragma unroll
+      for (int i = 0; i < WR; ++i) {
+        const double am = t == 0 ? cm[i * 8 + g] : 0.0;
+#pragma unroll
+        for (int j = 0; j < WN; ++j) dmma(acce[i][j][0], acce[i][j][1], am, bm[j]);
+      }
+    }
+    eo_epilogue<WR, WN, KCONTIG, true, SCAT, MIDFIX, false>(p, acce, acco, my_rt, rt0 * 8 + my_rt0 * 8, n0 + wn * WN * 8, g, t,
+                                                            cmid_s, umid_s + (ti & 1) * BN + wn * WN * 8);
     if (tracing) tr[2] = clock64();                              // epilogue done
   }
 }

@@ -52,7 +52,9 @@ __device__ __forceinline__ void split_column(int64_t nn, int64_t before, int64_t
 // column D[:, mid]) and umid_s (u[mid] of the tile's 64 columns, indexed by column - ncol_tile) then
 // come from shared memory (staged by the warp-specialised kernel), so no global load sits between
 // the accumulators and the stores.
-template <int WR, int WN, bool KCONTIG, bool VEC16, bool SCAT, bool MIDFIX>
+// MIDADD = false: the caller has already added the middle-column term to acce (the warp-specialised kernel does
+// it with one DMMA per accumulator tile: plain FMAs issued here queue behind the other warps' DMMAs).
+template <int WR, int WN, bool KCONTIG, bool VEC16, bool SCAT, bool MIDFIX, bool MIDADD = MIDFIX>
 __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR][WN][2], double (&acco)[WR][WN][2],
                                             int my_rt, int row0, int64_t ncol0, int g, int t,
                                             const double* cmid_s = nullptr, const double* umid_s = nullptr) {
@@ -90,7 +92,7 @@ __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR
         s1 *= p.scale[KCONTIG ? 0 : b0 + 1];
       }
       double um0 = 0.0, um1 = 0.0;
-      if (MIDFIX) {
+      if (MIDADD) {
         const double2 um = *reinterpret_cast<const double2*>(umid_s + (j * 8 + 2 * t));
         um0 = um.x;
         um1 = um.y;
@@ -100,7 +102,7 @@ __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR
 #pragma unroll
       for (int i = 0; i < WR; ++i, ylo += step, yhi -= step) {
         double e0 = acce[i][j][0], e1 = acce[i][j][1];
-        if (MIDFIX) {
+        if (MIDADD) {
           const double cm = cmid_s[row0 + i * 8 + g];      // shared memory: no preloaded array (registers are tight)
           e0 = __fma_rn(cm, um0, e0);
           e1 = __fma_rn(cm, um1, e1);
@@ -163,7 +165,7 @@ __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR
     }
     const int64_t l0 = a0 * p.slab + b0, l1 = a1 * p.slab + b1;
     double um0 = 0.0, um1 = 0.0;
-    if (MIDFIX) {
+    if (MIDADD) {
       const double2 um = *reinterpret_cast<const double2*>(umid_s + (j * 8 + 2 * t));   // umid_s already at the warp's columns
       um0 = um.x;
       um1 = um.y;
@@ -184,7 +186,7 @@ __device__ __forceinline__ void eo_epilogue(const EoParams& p, double (&acce)[WR
       const int hrow = row0 + i * 8 + g;
       if (hrow >= p.H) continue;
       double e0 = acce[i][j][0], e1 = acce[i][j][1];
-      if (MIDFIX) {
+      if (MIDADD) {
         const double cm = cmid_s[hrow];
         e0 = __fma_rn(cm, um0, e0);
         e1 = __fma_rn(cm, um1, e1);

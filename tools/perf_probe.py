@@ -159,7 +159,8 @@ if __name__ == "__main__":
         sys.exit(0)
     if what == "wsdbg":
         lib = _lib.load()
-        for mode in (1, 6, 1, 6):
+        modes = [int(m) for m in sys.argv[2].split(",")] if len(sys.argv) > 2 else (1, 6, 1, 6)
+        for mode in modes:
             lib.pt_debug_set_eo_ws(mode)
             print("== ws debug mode", mode, "(1 default, 6 no consumer stagger)")
             eo_variants("four", 1024, 1, (1024, 257), 0, 64, "cfg2 d/dx FourMat K2 n=1024", (True,))
@@ -168,6 +169,13 @@ if __name__ == "__main__":
             eo_variants("cheb", 2048, 1, (8192, 2048), 1, 1, "cfg5a-1/8 ChebMat K1 n=2048", (True,))
             eo_variants("cheb", 512, 2, (512, 512, 512), 1, 1, "cfg5b y K1 n=512", (True,))
         lib.pt_debug_set_eo_ws(1)
+        sys.exit(0)
+    if what == "ws257":
+        for _ in range(2):
+            eo_variants("cheb", 257, 2, (1024, 257), 1, 64, "cfg2 d2/dy2 ChebMat K1 n=257", (True,))
+            eo_variants("cheb", 255, 2, (1024, 255), 1, 64, "n=255", (True,))
+            eo_variants("cheb", 513, 2, (1024, 513), 1, 32, "n=513", (True,))
+            eo_variants("four", 1024, 1, (1024, 257), 0, 64, "cfg2 d/dx FourMat K2 n=1024", (True,))
         sys.exit(0)
     if what == "ws":
         eo_variants("four", 1024, 1, (1024, 257), 0, 64, "cfg2 d/dx FourMat K2 n=1024")
