@@ -280,6 +280,7 @@ dense_apply_kernel(const DenseParams p) {
 
   // ---- epilogue: Y = alpha*scale*acc + beta*Y ----------------------------------------------------
   const bool use_beta = (p.beta != 0.0);
+  const bool unit = p.scale_mode == PT_SCALE_NONE && p.alpha == 1.0;
 #pragma unroll
   for (int j = 0; j < WN; ++j) {
     const int64_t nn = n0 + (wn * WN + j) * 8 + 2 * t;  // this thread's first column
@@ -315,8 +316,10 @@ dense_apply_kernel(const DenseParams p) {
       if (row >= p.n_out) continue;
       double r0 = s0, r1 = s1;
       if (p.scale_mode == PT_SCALE_ROW) { const double sr = p.scale[row]; r0 *= sr; r1 *= sr; }
-      double v0 = __dmul_rn(r0, acc[i][j][0]);   // explicit roundings: every kernel variant gives the same bits
-      double v1 = __dmul_rn(r1, acc[i][j][1]);
+      // explicit roundings: every kernel variant gives the same bits.  alpha = 1 without scaling multiplies nothing
+      // (1 * x = x exactly): a plain FP64 instruction issued here queues behind the DMMAs of the CTA that shares the SM
+      double v0 = unit ? acc[i][j][0] : __dmul_rn(r0, acc[i][j][0]);
+      double v1 = unit ? acc[i][j][1] : __dmul_rn(r1, acc[i][j][1]);
       const int64_t off = int64_t(row) * p.before;
       const double* c0 = (SCAT ? p.C : p.Y) + l0 + off;
       const double* c1 = (SCAT ? p.C : p.Y) + l1 + off;

@@ -116,13 +116,16 @@ __device__ __forceinline__ double2 ldg2(const double* p) {
 }
 
 // ---- consumer: DMMAs of one staged chunk, specialised on the exact number of row tiles ------------
-template <int RT, bool KCONTIG>
-__device__ __forceinline__ void ws_compute(const double* As, const double* Et, const double* Ot, int npairs,
+// NPAIRS is a template parameter so that a full chunk is ONE straight-line block: the fragment loads of the second
+// panel pair can be scheduled under the DMMAs of the first (behind a run-time `pr < npairs` they could not, and a
+// consumer warp sat through the shared-memory latency once more per chunk).
+template <int RT, bool KCONTIG, int NPAIRS>
+__device__ __forceinline__ void ws_compute(const double* As, const double* Et, const double* Ot,
                                            int swz, const int (&bcol)[WN], double (&acce)[WR][WN][2],
                                            double (&acco)[WR][WN][2]) {
 #pragma unroll
-  for (int pr = 0; pr < 2; ++pr) {
-    if (pr < npairs) {
+  for (int pr = 0; pr < NPAIRS; ++pr) {
+    {
       double2 ae[WR], ao[WR], be[WN], bo[WN];
 #pragma unroll
       for (int i = 0; i < RT; ++i) {
@@ -164,8 +167,10 @@ struct WsDispatch {
   static __device__ __forceinline__ void run(int my_rt, const double* As, const double* Et, const double* Ot,
                                              int npairs, int swz, const int (&bcol)[WN], double (&acce)[WR][WN][2],
                                              double (&acco)[WR][WN][2]) {
-    if (my_rt == RT) ws_compute<RT, KCONTIG>(As, Et, Ot, npairs, swz, bcol, acce, acco);
-    else WsDispatch<RT - 1, KCONTIG>::run(my_rt, As, Et, Ot, npairs, swz, bcol, acce, acco);
+    if (my_rt == RT) {
+      if (npairs == 2) ws_compute<RT, KCONTIG, 2>(As, Et, Ot, swz, bcol, acce, acco);
+      else ws_compute<RT, KCONTIG, 1>(As, Et, Ot, swz, bcol, acce, acco);
+    } else WsDispatch<RT - 1, KCONTIG>::run(my_rt, As, Et, Ot, npairs, swz, bcol, acce, acco);
   }
 };
 template <bool KCONTIG>
