@@ -992,6 +992,60 @@ def extra_workloads(ctx, args, threads, recs):
 
             guarded(name, one)
 
+        def axis_solve():
+            """SURVEY 8f rank 4 under the same clock: (D2 - k^2) y = f with Dirichlet rows along y of the config-2 grid
+            (n = 257, 64 fields = 65 536 grid lines), factorisation form and one-pass inverse form."""
+            import numpy as np
+            import pytristan_b200 as pt
+            npts, batch, k2 = (1024, 257), 64, 4.0
+            x = pt.cheb(npts[1], -1.0, 1.0)
+            A = np.asarray(pt.ChebMat(x, order=2)) - k2 * np.eye(npts[1])
+            A[0] = 0.0; A[0, 0] = 1.0
+            A[-1] = 0.0; A[-1, -1] = 1.0
+            F = torch.randn(batch, npts[0] * npts[1], dtype=torch.float64, device="cuda")
+            Y = torch.empty_like(F)
+            R = torch.empty_like(F)
+            rec = {"workload": "axis_solve_1024x257_b64", "n_gpus": 1, "scaling": "single GPU", "npts": list(npts),
+                   "batch": batch, "what": "(D2 - 4) y = f, Dirichlet rows, along y for every grid line", "steps": steps}
+            a_norm = float(np.max(np.sum(np.abs(A), axis=1)))
+            torch.cuda.synchronize()
+            time.sleep(1.0)
+            for method in ("lu", "inverse"):
+                t0 = time.perf_counter()
+                solver = pt.AxisSolver(A, npts=npts, axis=1, method=method)
+                torch.cuda.synchronize()
+                setup = time.perf_counter() - t0
+                for _ in range(3):
+                    solver.solve(F, out=Y)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(steps):
+                    solver.solve(F, out=Y)
+                e1.record(); e1.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                R.copy_(F)
+                after, n, before = solver.matrix._split(F.numel())
+                solver.matrix._apply_device(Y.reshape(-1), after, n, before, R.reshape(-1), -1.0, 1.0, None, None)   # r = f - A y
+                eta = float(R.abs().max() / (a_norm * Y.abs().max() + F.abs().max()))
+                rec[method] = {"ms_per_solve": ms, "value": F.numel() / (ms * 1e-3), "unit": "points/s", "setup_s": setup,
+                               "normwise_backward_error": eta,
+                               "api": f"pytristan_b200.AxisSolver(A, npts, axis=1, method='{method}').solve(f, out=y)"}
+            if not args.no_cpu:
+                import scipy.linalg as sla
+                set_blas_threads()
+                lu = sla.lu_factor(A)
+                sample = 4
+                Fh = F[:sample].cpu().numpy().reshape(sample, npts[1], npts[0]).transpose(1, 0, 2).reshape(npts[1], -1)
+                t0 = time.perf_counter()
+                sla.lu_solve(lu, Fh)
+                dt = time.perf_counter() - t0
+                rec["cpu_baseline"] = {"value": sample * npts[0] * npts[1] / dt, "unit": "points/s", "cores": threads,
+                                       "kind": "port", "sample": f"scipy.linalg.lu_solve (LAPACK getrs) on {sample} of the {batch} fields"}
+            return rec
+
+        guarded("axis_solve_1024x257_b64", axis_solve)
+
 
 _REAL_STDOUT = None
 
