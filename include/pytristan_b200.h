@@ -352,6 +352,8 @@ int64_t pt_lu_plan_size(int n, int nb);
 int pt_lu_plan(const double* LU, int n, int nb, double* plan, pt_stream_t stream);
 int pt_lu_solve(const double* plan, const int32_t* perm, int n, int nb, const double* F, double* X, double* work,
                 int64_t after, int64_t before, pt_stream_t stream);
+/* tuning hook: grid lines per CTA of the substitution kernel (64 or 128; 0 = default) */
+int pt_debug_set_tri_lines(int lines);
 
 /* ---- measurement helper ------------------------------------------------------------------ */
 /* Register-resident DMMA loop: the FP64 tensor-core roofline denominator measured on the box.

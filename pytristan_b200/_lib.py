@@ -118,6 +118,7 @@ SIGNATURES = {
     "pt_lu_plan_size": (_c_i64, [_c_i32, _c_i32]),
     "pt_lu_plan": (_c_i32, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr]),
     "pt_lu_solve": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr]),
+    "pt_debug_set_tri_lines": (_c_i32, [_c_i32]),
     "pt_measure_dmma_peak": (_c_i32, [ctypes.POINTER(_c_f64), _c_i32]),
     "pt_peer_alloc": (_c_i32, [_c_i64, ctypes.POINTER(_c_ptr)]),
     "pt_peer_free": (_c_i32, [_c_ptr]),

@@ -206,10 +206,7 @@ __global__ void tri_pack_kernel(const double* __restrict__ LU, int n, int r0, in
 // fills it): a warp issuing plain FP64 instructions beside a warp that streams DMMAs on the same sub-partition
 // waits ~150 cycles per instruction for the pipe, so every sub-partition hosts exactly one warp.  In/Out address element (line nn, row r) at
 // (nn / before) * ld + r * before + nn % before; `reversed` mirrors the row order (upper factor).
-constexpr int TRI_TL = 128;
-constexpr int TRI_TLP = TRI_TL + 4;
 constexpr int TRI_PP = 20;                    // pitch of a staged triangle panel row (16 entries), = 4 mod 16
-constexpr int TRI_PANEL = 128 * TRI_PP;       // doubles of one panel buffer (up to 128 k rows)
 constexpr int TRI_MAXM = 128;
 
 __device__ __forceinline__ void tri_dmma(double& c0, double& c1, double a, double b) {
@@ -218,11 +215,12 @@ __device__ __forceinline__ void tri_dmma(double& c0, double& c1, double a, doubl
                : "d"(a), "d"(b));
 }
 
-template <bool UNIT>
-__global__ void __launch_bounds__(TRI_TL) tri_solve_kernel(const double* __restrict__ TT, int m, int m16, int reversed,
+template <bool UNIT, int TL>
+__global__ void __launch_bounds__(TL) tri_solve_kernel(const double* __restrict__ TT, int m, int m16, int reversed,
                                                            const double* __restrict__ In, int64_t ld_in,
                                                            double* __restrict__ Out, int64_t ld_out, int64_t NN,
                                                            int64_t before) {
+  constexpr int TRI_TL = TL, TRI_TLP = TL + 4;
   extern __shared__ __align__(16) double tile[];   // [m16][TRI_TLP], then two panel buffers
   double* panels = tile + m16 * TRI_TLP;
   const int tid = threadIdx.x;
@@ -234,7 +232,7 @@ __global__ void __launch_bounds__(TRI_TL) tri_solve_kernel(const double* __restr
   // rows of the triangle that sub-block s0 needs: TT[k][s0 .. s0+15] for k < s0 + 16 (the last 16 k are the
   // 16 x 16 triangle itself) — 16-byte cp.async into panel buffer (s0 / 16) & 1
   auto issue_panel = [&](int s0) {
-    double* pan = panels + ((s0 >> 4) & 1) * TRI_PANEL;
+    double* pan = panels + ((s0 >> 4) & 1) * (m16 * TRI_PP);
     const int pieces = (s0 + 16) * 8;
     for (int pc = tid; pc < pieces; pc += TRI_TL) {
       const int k = pc >> 3, c = (pc & 7) * 2;
@@ -274,7 +272,7 @@ __global__ void __launch_bounds__(TRI_TL) tri_solve_kernel(const double* __restr
     __syncthreads();                       // panel s0 (and the tile) landed; everyone is done with the other buffer
     if (s0 + 16 < m16) issue_panel(s0 + 16);
     ptdense::cp_async_commit();
-    const double* pan = panels + ((s0 >> 4) & 1) * TRI_PANEL;
+    const double* pan = panels + ((s0 >> 4) & 1) * (m16 * TRI_PP);
     if (s0 > 0) {
       double acc[2][4][2];
       // C fragment: row = s0 + 8 i + g, lines L0 + 8 j + 2 t4, +1 — the accumulators start as the rows themselves
@@ -368,7 +366,17 @@ inline int64_t packed_doubles(int n_out, int n_in) {
   return int64_t((n_in + 3) / 4) * (8 * ((int64_t(n_out) + 7) / 8)) * 4;
 }
 
-inline int64_t lu_block(int n, int nb, int b, LuBlock* out) {   // returns the offset past block b
+// Block rows actually used for a requested maximum of nb rows: n split into ceil(n / nb) nearly equal parts of a
+// multiple of 8 rows (n = 257, nb = 128: 88 + 88 + 81 instead of 128 + 128 + 1 — a one-row block costs two passes
+// over the fields for nothing).
+inline int lu_rows(int n, int nb) {
+  const int parts = (n + nb - 1) / nb;
+  const int bs = 8 * ((n + 8 * parts - 1) / (8 * parts));
+  return bs < nb ? bs : nb;
+}
+
+inline int64_t lu_block(int n, int nb_max, int b, LuBlock* out) {   // returns the offset past block b
+  const int nb = lu_rows(n, nb_max);
   int64_t off = 0;
   for (int i = 0; i <= b; ++i) {
     LuBlock k;
@@ -455,14 +463,16 @@ extern "C" int pt_lu_factor(const double* A, int n, double* LU, int32_t* perm, d
 
 extern "C" int64_t pt_lu_plan_size(int n, int nb) {
   if (n <= 0 || nb <= 0) return 0;
-  return lu_block(n, nb, (n + nb - 1) / nb - 1, nullptr);
+  const int bs = lu_rows(n, nb);
+  return lu_block(n, nb, (n + bs - 1) / bs - 1, nullptr);
 }
 
 extern "C" int pt_lu_plan(const double* LU, int n, int nb, double* plan, pt_stream_t stream) {
   PT_REQUIRE(LU && plan, "pt_lu_plan: null pointer");
   PT_REQUIRE(n >= 1 && nb >= 16 && nb <= 128 && nb % 16 == 0, "pt_lu_plan: bad n=%d / block size %d (16..128, multiple of 16)", n, nb);
   cudaStream_t st = pt::as_stream(stream);
-  const int nblk = (n + nb - 1) / nb;
+  const int bs = lu_rows(n, nb);
+  const int nblk = (n + bs - 1) / bs;
   for (int b = 0; b < nblk; ++b) {
     LuBlock k;
     lu_block(n, nb, b, &k);
@@ -484,25 +494,43 @@ extern "C" int pt_lu_plan(const double* LU, int n, int nb, double* plan, pt_stre
 }
 
 namespace {
-template <bool UNIT>
-int launch_tri_solve(const double* TT, const LuBlock& k, int reversed, const double* in, double* out, int64_t ld,
-                     int64_t after, int64_t before, cudaStream_t st) {
-  auto kern = tri_solve_kernel<UNIT>;
-  const size_t smem = (size_t(k.m16) * TRI_TLP + 2 * TRI_PANEL) * sizeof(double);
+int g_tri_tl = 0;      // tuning hook (pt_debug_set_tri_lines): 0 = by shape, 64 or 128 = lines per CTA
+
+template <bool UNIT, int TL>
+int launch_tri_solve_tl(const double* TT, const LuBlock& k, int reversed, const double* in, double* out, int64_t ld,
+                        int64_t after, int64_t before, cudaStream_t st) {
+  auto kern = tri_solve_kernel<UNIT, TL>;
+  const size_t smem = size_t(k.m16) * (TL + 4 + 2 * TRI_PP) * sizeof(double);
   static bool attr_set[64] = {false};
   int dev = 0;
   PT_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int((size_t(TRI_MAXM) * TRI_TLP + 2 * TRI_PANEL) * sizeof(double))));
+    PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(size_t(TRI_MAXM) * (TL + 4 + 2 * TRI_PP) * sizeof(double))));
     attr_set[dev] = true;
   }
   const int64_t NN = after * before;
-  const int64_t grid = (NN + TRI_TL - 1) / TRI_TL;
+  const int64_t grid = (NN + TL - 1) / TL;
   if (grid > 2147483647LL) return pt::fail(PT_ERR_UNSUPPORTED, "pt_lu_solve: grid too large");
-  kern<<<unsigned(grid), TRI_TL, smem, st>>>(TT, k.m, k.m16, reversed, in, ld, out, ld, NN, before);
+  kern<<<unsigned(grid), TL, smem, st>>>(TT, k.m, k.m16, reversed, in, ld, out, ld, NN, before);
   return pt::check_launch("pt_lu_solve");
 }
+
+// 64 lines per CTA: two or three CTAs share an SM, so that the loads and stores of one overlap the substitution of
+// another (one warp per sub-partition and CTA); 128 lines when that would not fill the GPU anyway
+template <bool UNIT>
+int launch_tri_solve(const double* TT, const LuBlock& k, int reversed, const double* in, double* out, int64_t ld,
+                     int64_t after, int64_t before, cudaStream_t st) {
+  const int tl = g_tri_tl ? g_tri_tl : 64;
+  if (tl == 64) return launch_tri_solve_tl<UNIT, 64>(TT, k, reversed, in, out, ld, after, before, st);
+  return launch_tri_solve_tl<UNIT, 128>(TT, k, reversed, in, out, ld, after, before, st);
+}
 }  // namespace
+
+extern "C" int pt_debug_set_tri_lines(int lines) {
+  g_tri_tl = (lines == 64 || lines == 128) ? lines : 0;
+  return PT_OK;
+}
 
 extern "C" int pt_lu_solve(const double* plan, const int32_t* perm, int n, int nb, const double* F, double* X,
                            double* work, int64_t after, int64_t before, pt_stream_t stream) {
@@ -512,7 +540,8 @@ extern "C" int pt_lu_solve(const double* plan, const int32_t* perm, int n, int n
   PT_REQUIRE(F != X && F != work && X != work, "pt_lu_solve: F, X and work must be distinct");
   if (after == 0) return PT_OK;
   cudaStream_t st = pt::as_stream(stream);
-  const int nblk = (n + nb - 1) / nb;
+  const int bs = lu_rows(n, nb);
+  const int nblk = (n + bs - 1) / bs;
   const int64_t ld = int64_t(n) * before;
   const int64_t total = after * ld;
   // X <- P F

@@ -152,6 +152,8 @@ def solve_probe(n, npts, axis, batch, label, blocks=(32, 64, 128)):
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what == "solve":
+        if len(sys.argv) > 2:
+            _lib.load().pt_debug_set_tri_lines(int(sys.argv[2]))
         solve_probe(257, (1024, 257), 1, 64, "cfg2 y-solve n=257 (strided axis)")
         solve_probe(1024, (1024, 257), 0, 64, "cfg2 x-solve n=1024 (contiguous axis)")
         solve_probe(512, (512, 512, 512), 1, 1, "512^3 y-solve n=512")
