@@ -285,3 +285,30 @@ def test_lu_oracle_vs_lapack(n):
         assert np.max(np.abs(back - F)) <= 1e-12 * np.linalg.cond(A) * np.max(np.abs(F))
     with pytest.raises(np.linalg.LinAlgError):
         oracle.lu_factor(np.ones((3, 3)))
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 8, 33, 128])
+def test_cheb_mat_vs_published_closed_form(N):
+    """Trefethen, Spectral Methods in MATLAB (2000), Theorem 7 (eqs. 6.3-6.5), written out entry by entry — an
+    implementation that shares nothing with oracle.cheb_mat (which uses the negative-sum trick and the flipping
+    trick) — plus the two matrices printed in the book (p. 53)."""
+    x = oracle.cheb_nodes(N + 1)
+    D = oracle.cheb_mat(x, 1)
+    c = np.ones(N + 1); c[0] = c[N] = 2.0
+    ref = np.zeros((N + 1, N + 1))
+    for i in range(N + 1):
+        for j in range(N + 1):
+            if i != j:
+                ref[i, j] = (c[i] / c[j]) * (-1.0) ** (i + j) / (x[i] - x[j])
+            elif i == 0:
+                ref[i, j] = (2.0 * N * N + 1.0) / 6.0
+            elif i == N:
+                ref[i, j] = -(2.0 * N * N + 1.0) / 6.0
+            else:
+                ref[i, j] = -x[j] / (2.0 * (1.0 - x[j] ** 2))
+    scale = np.sum(np.abs(ref), axis=1, keepdims=True)
+    assert np.max(np.abs(D - ref) / scale) <= 1e-13 * max(1, N)          # the closed-form diagonal loses ~N eps itself
+    if N == 1:
+        assert np.array_equal(D, np.array([[0.5, -0.5], [0.5, -0.5]]))
+    if N == 2:
+        assert np.max(np.abs(D - np.array([[1.5, -2.0, 0.5], [0.5, 0.0, -0.5], [-0.5, 2.0, -1.5]]))) <= 2e-15
