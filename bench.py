@@ -1025,8 +1025,7 @@ def extra_workloads(ctx, args, threads, recs):
                 e1.record(); e1.synchronize()
                 ms = e0.elapsed_time(e1) / steps
                 R.copy_(F)
-                after, n, before = solver.matrix._split(F.numel())
-                solver.matrix._apply_device(Y.reshape(-1), after, n, before, R.reshape(-1), -1.0, 1.0, None, None)   # r = f - A y
+                solver.matrix.apply(Y, out=R, alpha=-1.0, beta=1.0)                                  # r = f - A y
                 eta = float(R.abs().max() / (a_norm * Y.abs().max() + F.abs().max()))
                 rec[method] = {"ms_per_solve": ms, "value": F.numel() / (ms * 1e-3), "unit": "points/s", "setup_s": setup,
                                "normwise_backward_error": eta,
