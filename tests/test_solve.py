@@ -256,3 +256,23 @@ def test_dense_apply_on_row_ranges(after, before):
     assert np.max(np.abs(got - ref)[:, q0:q0 + n_out] / bound) <= 1e-14
     assert lib.pt_dense_apply_ld(_lib.dptr(packed), n_out, n_in, d_U.data_ptr(), n_in * before - 1, d_Y.data_ptr(), ld,
                                  after, before, 1.0, 0.0, _lib.stream_ptr()) != 0
+
+
+def test_lu_solve_large_n_is_normwise_backward_stable():
+    """n = 2000 (16 block rows of 125 -> 128 rows, multi-level off-diagonal products): normwise backward error at
+    the n * eps level and agreement with LAPACK to the conditioning."""
+    import torch
+
+    import pytristan_b200 as pt
+
+    n, lines = 2000, 24
+    rng = np.random.default_rng(7)
+    A = rng.standard_normal((n, n)) + 0.1 * np.sqrt(n) * np.eye(n)
+    solver = pt.AxisSolver(A, npts=(lines, n), axis=1)
+    F = rng.standard_normal((1, lines * n))
+    y = solver.solve(torch.from_numpy(F).cuda()).cpu().numpy()
+    r = oracle.apply_along_axis(A, y, (lines, n), 1) - F
+    eta = np.max(np.abs(r)) / (np.max(np.sum(np.abs(A), axis=1)) * np.max(np.abs(y)) + np.max(np.abs(F)))
+    assert eta <= n * np.finfo(np.float64).eps, eta
+    ref = oracle.solve_along_axis(A, F, (lines, n), 1)
+    assert np.max(np.abs(y - ref)) <= 1e-13 * np.linalg.cond(A) * np.max(np.abs(ref))
